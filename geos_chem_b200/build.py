@@ -1,0 +1,77 @@
+"""Build recipe for libgckpp_b200.so (sm_100a only) -- explicit nvcc, in-tree output.
+
+Steps: (1) kppgen emits gen/*.h, gen/*.cuh from the committed mechanism IR;
+(2) each .cu is compiled to an object with `-gencode arch=compute_100a,code=sm_100a -lineinfo`;
+(3) objects are linked into geos_chem_b200/libgckpp_b200.so (plain C ABI, no torch).
+Objects are rebuilt only when a source/dependency is newer.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+GEN = os.path.join(CSRC, "gen")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libgckpp_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+# translation unit -> extra flags
+UNITS = {
+    "gckpp_gpu.cu": [],
+    "kernels_misc.cu": [],
+    # arithmetic-reference kernel: no FMA contraction so sums round like the reference's
+    "ros_generic.cu": ["-fmad=false"],
+}
+
+
+def _newer(src_list, target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in src_list if os.path.exists(s))
+
+
+def generate():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from geos_chem_b200.kppgen import emit_cuda
+    emit_cuda.main(["--out", GEN])
+
+
+def build(verbose=False):
+    generate()
+    os.makedirs(OBJ, exist_ok=True)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps += [os.path.join(GEN, f) for f in os.listdir(GEN)]
+    deps.append(os.path.join(HERE, "..", "include", "gckpp_gpu.h"))
+    objs = []
+    logs = []
+    procs = []
+    for unit, extra in UNITS.items():
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if _newer([src] + deps, obj):
+            cmd = [NVCC] + ARCH + COMMON + extra + ["-c", src, "-o", obj]
+            procs.append((unit, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for unit, cmd, p in procs:
+        out, _ = p.communicate()
+        logs.append("$ " + " ".join(cmd) + "\n" + out)
+        if p.returncode != 0:
+            sys.stderr.write(logs[-1])
+            raise RuntimeError("nvcc failed for " + unit)
+    if procs or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        subprocess.check_call(cmd)
+    if logs:
+        with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+            f.write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv))

@@ -1,0 +1,665 @@
+// C ABI of the B200 KPP chemistry path (see include/gckpp_gpu.h for the contract and the
+// reference interfaces each entry point replaces).  Host side only: option decoding
+// (= Rosenbrock(), gckpp_Integrator.F90:165-531), buffer management, kernel launches.
+// There is NO CPU fallback: every entry point fails loudly if CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gckpp_gpu.h"
+#include "ros_common.cuh"
+#include "kernels.h"
+
+#include "gen/fullchem_tables.h"
+#include "gen/Hg_tables.h"
+#include "gen/carbon_tables.h"
+#include "gen/fullchem_names.h"
+#include "gen/Hg_names.h"
+#include "gen/carbon_names.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(-(1000 + (int)e_), "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+static const gckpp_host_tables_t *host_tables(int mech_id)
+{
+  switch (mech_id) {
+  case GCKPP_MECH_FULLCHEM: return &fullchem_tables;
+  case GCKPP_MECH_HG: return &Hg_tables;
+  case GCKPP_MECH_CARBON: return &carbon_tables;
+  default: return nullptr;
+  }
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n)
+  {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return (int)e;
+    bytes = n;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T *as() { return (T *)p; }
+};
+
+struct gckpp_gpu_handle {
+  int mech_id = 0, device = 0, max_cells = 0;
+  const gckpp_host_tables_t *T = nullptr;
+  MechDev M{};
+  std::vector<void *> table_allocs;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  int sm_count = 0;
+  // integrator launch geometry + workspace
+  int threads = 128, blocks_per_sm = 2, max_blocks = 0;
+  WsLayout L{};
+  DevBuf work, next, sums, tol, cell_list, counter, rconst_work, scratch;
+  // staging for the host entry points
+  DevBuf s_conc_in, s_conc_out, s_rconst, s_met, s_photol, s_khet, s_hstart, s_active, s_ist, s_rst, s_ierr;
+  int opt_retry = 0, opt_kernel = -1, opt_sort = 0;
+  double stats[16]{};
+};
+
+extern "C" const char *gckpp_gpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int gckpp_gpu_dims(int mech_id, int32_t *dims)
+{
+  const gckpp_host_tables_t *T = host_tables(mech_id);
+  if (!T || !dims) return fail(-10, "gckpp_gpu_dims: bad mechanism id %d", mech_id);
+  dims[0] = T->nvar; dims[1] = T->nfix; dims[2] = T->nspec; dims[3] = T->nreact;
+  dims[4] = T->nnz; dims[5] = T->nphot; dims[6] = T->next;
+  return 0;
+}
+
+extern "C" const char *gckpp_gpu_spc_name(int mech_id, int i)
+{
+  const gckpp_host_tables_t *T = host_tables(mech_id);
+  if (!T || i < 0 || i >= T->nspec) return nullptr;
+  switch (mech_id) {
+  case GCKPP_MECH_FULLCHEM: return fullchem_spc_names[i];
+  case GCKPP_MECH_HG: return Hg_spc_names[i];
+  default: return carbon_spc_names[i];
+  }
+}
+
+template <class T> static int upload(gckpp_gpu_handle *h, const T *src, size_t n, const T **dst)
+{
+  void *p = nullptr;
+  if (n == 0) n = 1;
+  CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+  h->table_allocs.push_back(p);
+  if (src) CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = (const T *)p;
+  return 0;
+}
+
+static WsLayout make_layout(const gckpp_host_tables_t *T)
+{
+  WsLayout L;
+  int o = 0;
+  L.Y = o;  o += T->nspec;
+  L.YN = o; o += T->nspec;
+  L.F0 = o; o += T->nvar;
+  L.FC = o; o += T->nvar;
+  L.K = o;  o += 6 * T->nvar;           // up to 6 stages (Rodas4)
+  L.G = o;  o += T->nnz > 0 ? T->nnz : 1;
+  L.RC = o; o += T->nreact;
+  L.AB = o; o += (T->nreact > T->nb ? T->nreact : T->nb);
+  L.W = o;  o += T->nvar;
+  L.total = o;
+  return L;
+}
+
+extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_handle_t **out)
+{
+  if (!out) return fail(-10, "gckpp_gpu_init: handle pointer is NULL");
+  *out = nullptr;
+  const gckpp_host_tables_t *T = host_tables(mech_id);
+  if (!T) return fail(-10, "gckpp_gpu_init: bad mechanism id %d", mech_id);
+  if (max_cells <= 0) return fail(-10, "gckpp_gpu_init: max_cells must be positive");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(-10, "gckpp_gpu_init: device %d of %d", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  gckpp_gpu_handle *h = new gckpp_gpu_handle();
+  h->mech_id = mech_id; h->device = device; h->max_cells = max_cells; h->T = T;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto &e : h->ev) CUDA_TRY(cudaEventCreate(&e));
+  MechDev &M = h->M;
+  M.nvar = T->nvar; M.nfix = T->nfix; M.nspec = T->nspec; M.nreact = T->nreact; M.nnz = T->nnz;
+  M.nb = T->nb; M.nphot = T->nphot; M.next = T->next; M.fun_split = T->fun_split;
+  int rc;
+#define UP(field, src, n, type) if ((rc = upload<type>(h, (const type *)(src), (size_t)(n), (const type **)&M.field))) { gckpp_gpu_finalize(h); return rc; }
+  UP(a_term, T->a_term, T->nreact, int4);
+  UP(p_ptr, T->p_ptr, T->nvar + 1, int); UP(p_coef, T->p_coef, T->np, double); UP(p_rxn, T->p_rxn, T->np, int);
+  UP(d_ptr, T->d_ptr, T->nvar + 1, int); UP(d_term, T->d_term, T->nd, int4);
+  UP(v_ptr, T->v_ptr, T->nvar + 1, int); UP(v_coef, T->v_coef, T->nv, double); UP(v_rxn, T->v_rxn, T->nv, int);
+  if (T->nnz > 0) {
+    UP(crow, T->crow, T->nvar + 1, int); UP(diag, T->diag, T->nvar, int); UP(icol, T->icol, T->nnz, int);
+    UP(b_term, T->b_term, T->nb, int4);
+    UP(j_ptr, T->j_ptr, T->nnz + 1, int); UP(j_coef, T->j_coef, T->nj, double); UP(j_b, T->j_b, T->nj, int);
+  }
+  UP(lit, T->lit, T->nlit, double);
+#undef UP
+  h->L = make_layout(T);
+  h->max_blocks = h->sm_count * h->blocks_per_sm;
+  if (h->next.ensure(sizeof(int)) || h->sums.ensure(8 * sizeof(unsigned long long)) ||
+      h->tol.ensure(2 * sizeof(double) * T->nvar) || h->counter.ensure(4 * sizeof(int))) {
+    gckpp_gpu_finalize(h);
+    return fail(-1002, "gckpp_gpu_init: out of device memory");
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
+{
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void *p : h->table_allocs) cudaFree(p);
+  DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
+                    &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
+                    &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_set_option(gckpp_gpu_handle_t *h, const char *key, int value)
+{
+  if (!h || !key) return fail(-10, "gckpp_gpu_set_option: NULL argument");
+  if (!strcmp(key, "retry")) h->opt_retry = value;
+  else if (!strcmp(key, "kernel")) h->opt_kernel = value;
+  else if (!strcmp(key, "sort")) h->opt_sort = value;
+  else if (!strcmp(key, "blocks_per_sm")) { if (value < 1 || value > 16) return fail(-10, "blocks_per_sm out of range"); h->blocks_per_sm = value; h->max_blocks = h->sm_count * value; }
+  else if (!strcmp(key, "threads")) { if (value < 32 || value > 1024 || value % 32) return fail(-10, "threads must be a multiple of 32"); h->threads = value; }
+  else return fail(-10, "gckpp_gpu_set_option: unknown option '%s'", key);
+  return 0;
+}
+
+// ---- Rosenbrock(): option decoding (gckpp_Integrator.F90:165-531 after Integrate's merge :100-117)
+static void set_method(RosOpts &o, int id)
+{
+  memset(o.A, 0, sizeof o.A); memset(o.C, 0, sizeof o.C); memset(o.M, 0, sizeof o.M);
+  memset(o.E, 0, sizeof o.E); memset(o.Alpha, 0, sizeof o.Alpha); memset(o.Gamma, 0, sizeof o.Gamma);
+  memset(o.NewF, 0, sizeof o.NewF);
+  switch (id) {
+  case 1: {  // Ros2 (:2062-2105)
+    double g = 1.0 + 1.0 / sqrt(2.0);
+    o.S = 2; o.A[0] = 1.0 / g; o.C[0] = -2.0 / g; o.NewF[0] = o.NewF[1] = 1;
+    o.M[0] = 3.0 / (2.0 * g); o.M[1] = 1.0 / (2.0 * g); o.E[0] = 1.0 / (2.0 * g); o.E[1] = 1.0 / (2.0 * g);
+    o.ELO = 2.0; o.Alpha[1] = 1.0; o.Gamma[0] = g; o.Gamma[1] = -g;
+    break; }
+  case 2:    // Ros3 (:2108-2157)
+    o.S = 3; o.A[0] = 1.0; o.A[1] = 1.0;
+    o.C[0] = -0.10156171083877702091975600115545e+01; o.C[1] = 0.40759956452537699824805835358067e+01;
+    o.C[2] = 0.92076794298330791242156818474003e+01;
+    o.NewF[0] = o.NewF[1] = 1;
+    o.M[0] = 0.1e+01; o.M[1] = 0.61697947043828245592553615689730e+01; o.M[2] = -0.42772256543218573326238373806514;
+    o.E[0] = 0.5; o.E[1] = -0.29079558716805469821718236208017e+01; o.E[2] = 0.22354069897811569627360909276199;
+    o.ELO = 3.0;
+    o.Alpha[1] = o.Alpha[2] = 0.43586652150845899941601945119356;
+    o.Gamma[0] = 0.43586652150845899941601945119356; o.Gamma[1] = 0.24291996454816804366592249683314;
+    o.Gamma[2] = 0.21851380027664058511513169485832e+01;
+    break;
+  case 3:    // Ros4 (:2164-2231)
+    o.S = 4;
+    o.A[0] = 0.2000000000000000e+01; o.A[1] = 0.1867943637803922e+01; o.A[2] = 0.2344449711399156;
+    o.A[3] = o.A[1]; o.A[4] = o.A[2];
+    o.C[0] = -0.7137615036412310e+01; o.C[1] = 0.2580708087951457e+01; o.C[2] = 0.6515950076447975;
+    o.C[3] = -0.2137148994382534e+01; o.C[4] = -0.3214669691237626; o.C[5] = -0.6949742501781779;
+    o.NewF[0] = o.NewF[1] = o.NewF[2] = 1;
+    o.M[0] = 0.2255570073418735e+01; o.M[1] = 0.2870493262186792; o.M[2] = 0.4353179431840180; o.M[3] = 0.1093502252409163e+01;
+    o.E[0] = -0.2815431932141155; o.E[1] = -0.7276199124938920e-01; o.E[2] = -0.1082196201495311; o.E[3] = -0.1093502252409163e+01;
+    o.ELO = 4.0;
+    o.Alpha[1] = 0.1145640000000000e+01; o.Alpha[2] = o.Alpha[3] = 0.6552168638155900;
+    o.Gamma[0] = 0.5728200000000000; o.Gamma[1] = -0.1769193891319233e+01; o.Gamma[2] = 0.7592633437920482;
+    o.Gamma[3] = -0.1049021087100450;
+    break;
+  case 5:    // Rodas4 (:2310-2405)
+    o.S = 6;
+    o.Alpha[1] = 0.386; o.Alpha[2] = 0.210; o.Alpha[3] = 0.630; o.Alpha[4] = o.Alpha[5] = 1.0;
+    o.Gamma[0] = 0.25; o.Gamma[1] = -0.1043; o.Gamma[2] = 0.1035; o.Gamma[3] = -0.3620000000000023e-01;
+    o.A[0] = 0.1544000000000000e+01; o.A[1] = 0.9466785280815826; o.A[2] = 0.2557011698983284;
+    o.A[3] = 0.3314825187068521e+01; o.A[4] = 0.2896124015972201e+01; o.A[5] = 0.9986419139977817;
+    o.A[6] = 0.1221224509226641e+01; o.A[7] = 0.6019134481288629e+01; o.A[8] = 0.1253708332932087e+02;
+    o.A[9] = -0.6878860361058950; o.A[10] = o.A[6]; o.A[11] = o.A[7]; o.A[12] = o.A[8]; o.A[13] = o.A[9]; o.A[14] = 1.0;
+    o.C[0] = -0.5668800000000000e+01; o.C[1] = -0.2430093356833875e+01; o.C[2] = -0.2063599157091915;
+    o.C[3] = -0.1073529058151375; o.C[4] = -0.9594562251023355e+01; o.C[5] = -0.2047028614809616e+02;
+    o.C[6] = 0.7496443313967647e+01; o.C[7] = -0.1024680431464352e+02; o.C[8] = -0.3399990352819905e+02;
+    o.C[9] = 0.1170890893206160e+02; o.C[10] = 0.8083246795921522e+01; o.C[11] = -0.7981132988064893e+01;
+    o.C[12] = -0.3152159432874371e+02; o.C[13] = 0.1631930543123136e+02; o.C[14] = -0.6058818238834054e+01;
+    o.M[0] = o.A[6]; o.M[1] = o.A[7]; o.M[2] = o.A[8]; o.M[3] = o.A[9]; o.M[4] = 1.0; o.M[5] = 1.0;
+    o.E[5] = 1.0;
+    for (int i = 0; i < 6; i++) o.NewF[i] = 1;
+    o.ELO = 4.0;
+    break;
+  case 6:    // Rang3 (:2412-2476)
+    o.S = 4;
+    o.A[0] = 5.09052051067020e+00; o.A[1] = 5.09052051067020e+00; o.A[2] = 0.0;
+    o.A[3] = 4.97628111010787e+00; o.A[4] = 2.77268164715849e-02; o.A[5] = 2.29428036027904e-01;
+    o.C[0] = -1.16790812312283e+01; o.C[1] = -1.64057326467367e+01; o.C[2] = -2.77268164715850e-01;
+    o.C[3] = -8.38103960500476e+00; o.C[4] = -8.48328409199343e-01; o.C[5] = 2.87009860433106e-01;
+    o.M[0] = 5.22582761233094e+00; o.M[1] = -5.56971148154165e-01; o.M[2] = 3.57979469353645e-01; o.M[3] = 1.72337398521064e+00;
+    o.E[0] = -5.16845212784040e+00; o.E[1] = -1.26351942603842e+00; o.E[2] = -1.11022302462516e-16; o.E[3] = 2.22044604925031e-16;
+    o.Alpha[1] = 2.21878746765329e+00; o.Alpha[2] = 2.21878746765329e+00; o.Alpha[3] = 1.55392337535788e+00;
+    o.Gamma[0] = 4.35866521508459e-01; o.Gamma[1] = -1.78292094614483e+00; o.Gamma[2] = -2.46541900496934e+00;
+    o.Gamma[3] = -8.05529997906370e-01;
+    for (int i = 0; i < 4; i++) o.NewF[i] = 1;
+    o.ELO = 3.0;
+    break;
+  default:   // 0, 4: Rodas3 (:2239-2303) -- the method GEOS-Chem selects
+    o.S = 4;
+    o.A[1] = 2.0; o.A[3] = 2.0; o.A[5] = 1.0;
+    o.C[0] = 4.0; o.C[1] = 1.0; o.C[2] = -1.0; o.C[3] = 1.0; o.C[4] = -1.0; o.C[5] = -(8.0 / 3.0);
+    o.NewF[0] = 1; o.NewF[2] = 1; o.NewF[3] = 1;
+    o.M[0] = 2.0; o.M[2] = 1.0; o.M[3] = 1.0;
+    o.E[3] = 1.0;
+    o.ELO = 3.0;
+    o.Alpha[2] = 1.0; o.Alpha[3] = 1.0;
+    o.Gamma[0] = 0.5; o.Gamma[1] = 1.5;
+    break;
+  }
+}
+
+struct Decoded {
+  RosOpts o;
+  int ICNTRL[20];
+  double RCNTRL[20];
+  int autoreduce;
+};
+
+// returns 0 or the reference's IERR (-1..-5); -12 = unsupported option combination
+static int decode_options(const gckpp_host_tables_t *T, double tin, double tout, const int32_t *icntrl_u,
+                          const double *rcntrl_u, const double *atol, const double *rtol, Decoded &d)
+{
+  int *IC = d.ICNTRL;
+  double *RC = d.RCNTRL;
+  for (int i = 0; i < 20; i++) { IC[i] = 0; RC[i] = 0.0; }
+  IC[14] = 5;
+  if (icntrl_u) for (int i = 0; i < 20; i++) if (icntrl_u[i] != 0) IC[i] = icntrl_u[i];
+  if (rcntrl_u) for (int i = 0; i < 20; i++) if (rcntrl_u[i] > 0) RC[i] = rcntrl_u[i];
+  if (IC[14] != -1) return fail(-12, "ICNTRL(15) must be -1: rates are not refreshed inside the integrator (got %d)", IC[14]);
+  RosOpts &o = d.o;
+  o.Autonomous = !(IC[0] == 0);
+  o.VectorTol = (IC[1] == 0);
+  int UplimTol = o.VectorTol ? T->nvar : 1;
+  if (IC[2] < 0 || IC[2] > 6) return fail(-2, "Selected Rosenbrock method not implemented: ICNTRL(3)=%d", IC[2]);
+  set_method(o, IC[2]);
+  if (IC[3] == 0) o.Max_no_steps = 200000;
+  else if (IC[3] > 0) o.Max_no_steps = IC[3];
+  else return fail(-1, "Improper value for maximal no of steps: ICNTRL(4)=%d", IC[3]);
+  d.autoreduce = (IC[11] == 1);
+  o.ClipNegative = (IC[15] == 1);
+  {  // WLAMCH('E') (gckpp_LinearAlgebra.F90:3861-3895) = 2^-52
+    o.Roundoff = DBL_EPSILON;
+  }
+  o.Hmin = RC[0];                       // RCNTRL > 0 merged above, negative values cannot reach here
+  o.Hmax = (RC[1] == 0.0) ? fabs(tout - tin) : fmin(fabs(RC[1]), fabs(tout - tin));
+  o.Hstart_rcntrl = RC[2];
+  o.FacMin = (RC[3] == 0.0) ? 0.2 : RC[3];
+  o.FacMax = (RC[4] == 0.0) ? 6.0 : RC[4];
+  o.FacRej = (RC[5] == 0.0) ? 0.1 : RC[5];
+  o.FacSafe = (RC[6] == 0.0) ? 0.9 : RC[6];
+  if (T->nnz > 0) {
+    if (!atol || !rtol) return fail(-10, "atol/rtol are required");
+    for (int i = 0; i < UplimTol; i++)
+      if ((atol[i] <= 0.0) || (rtol[i] <= 10.0 * o.Roundoff) || (rtol[i] >= 1.0))
+        return fail(-5, "Improper tolerance values: AbsTol(%d)=%g RelTol(%d)=%g", i + 1, atol[i], i + 1, rtol[i]);
+  }
+  o.Tstart = tin; o.Tend = tout;
+  o.Direction = (tout >= tin) ? +1 : -1;
+  return 0;
+}
+
+// ---- device-side helpers implemented in kernels_misc.cu
+static int ensure_workspace(gckpp_gpu_handle *h, int blocks)
+{
+  size_t nwarps = (size_t)blocks * (h->threads / 32);
+  size_t stride = (size_t)h->L.total * 32;
+  size_t bytes = nwarps * stride * sizeof(double);
+  if (bytes > h->work.bytes) {
+    if (h->work.ensure(bytes)) return fail(-1002, "out of device memory for the integrator workspace (%zu MB)", bytes >> 20);
+    cudaMemsetAsync(h->work.p, 0, bytes, h->stream);
+  }
+  return 0;
+}
+
+static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int nwork, const int *cell_list,
+                          const double *conc_in, const double *rconst, const double *hstart,
+                          double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+{
+  if (nwork <= 0) return 0;
+  int blocks = (nwork + h->threads - 1) / h->threads;
+  if (blocks > h->max_blocks) blocks = h->max_blocks;
+  int rc = ensure_workspace(h, blocks);
+  if (rc) return rc;
+  RosArgs a;
+  a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
+  a.conc_in = conc_in; a.rconst = rconst; a.hstart = hstart;
+  a.atol = h->tol.as<double>(); a.rtol = h->tol.as<double>() + h->T->nvar;
+  a.conc_out = conc_out; a.istatus = istatus; a.rstatus = rstatus; a.ierr = ierr;
+  a.work = h->work.as<double>(); a.ws_stride = (size_t)h->L.total * 32;
+  a.next = h->next.as<int>(); a.sums = h->sums.as<unsigned long long>();
+  a.L = h->L; a.o = d.o;
+  CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
+  if (h->T->nnz == 0) {   // carbon: forward Euler
+    CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
+  } else {
+    CUDA_TRY(launch_ros_generic(h->M, a, blocks, h->threads, h->stream));
+  }
+  h->stats[6] += 1;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, double tin, double tout,
+                                          const double *conc_in, const double *rconst,
+                                          const double *temp, const double *numden, const double *h2o,
+                                          const double *photol, const double *khet,
+                                          const double *atol, const double *rtol,
+                                          const int32_t *icntrl, const double *rcntrl,
+                                          const double *hstart, const uint8_t *active,
+                                          double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+{
+  if (!h) return fail(-10, "NULL handle");
+  if (ncell < 0 || !conc_in || !conc_out) return fail(-10, "gckpp_gpu_integrate: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  Decoded d;
+  int rc = decode_options(T, tin, tout, icntrl, rcntrl, atol, rtol, d);
+  if (rc) {
+    if (ierr && rc >= -5) CUDA_TRY(launch_fill_int(ierr, ncell, rc, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return rc;
+  }
+  if (d.autoreduce) return fail(-12, "auto-reduce (ICNTRL(12)=1) is not available in this build");
+  for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
+  if (atol && rtol) {
+    CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 8 * sizeof(unsigned long long), h->stream));
+
+  // K1: rate constants
+  CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+  if (!rconst) {
+    if (!temp || !numden || !h2o) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
+    if (h->rconst_work.ensure(sizeof(double) * (size_t)T->nreact * ncell)) return fail(-1002, "out of device memory for rconst");
+    CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, h->rconst_work.as<double>(), h->stream));
+    h->stats[6] += 1;
+    rconst = h->rconst_work.as<double>();
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+
+  // cells outside the chemistry grid: copy through, zero status
+  const int *cell_list = nullptr;
+  int nwork = ncell;
+  if (active) {
+    if (h->cell_list.ensure(sizeof(int) * (size_t)ncell)) return fail(-1002, "out of device memory");
+    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+    CUDA_TRY(launch_select_active(ncell, active, T->nspec, conc_in, conc_out, istatus, rstatus, ierr,
+                                  h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
+    h->stats[6] += 1;
+    CUDA_TRY(cudaMemcpyAsync(&nwork, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cell_list = h->cell_list.as<int>();
+  }
+  rc = run_integrator(h, d, ncell, nwork, cell_list, conc_in, rconst, hstart, conc_out, istatus, rstatus, ierr);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+
+  unsigned long long sums[8];
+  CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  int nfail = (int)sums[2], nfail2 = 0;
+  h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
+
+  // Do_FullChem's retry (fullchem_mod.F90:1138-1162): RCNTRL(3)=0, C restored, integrate again
+  if (h->opt_retry && nfail > 0 && ierr) {
+    if (h->cell_list.ensure(sizeof(int) * (size_t)ncell)) return fail(-1002, "out of device memory");
+    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+    CUDA_TRY(launch_select_failed(ncell, ierr, h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
+    int nretry = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nretry, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    Decoded d2 = d;
+    d2.o.Hstart_rcntrl = 0.0;
+    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    rc = run_integrator(h, d2, ncell, nretry, h->cell_list.as<int>(), conc_in, rconst, nullptr, conc_out, istatus, rstatus, ierr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    nfail2 = (int)sums[2];
+    h->stats[4] = nretry; h->stats[5] = nfail2;
+    h->stats[6] += 1;
+  } else {
+    h->stats[5] = 0;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->stats[0] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->stats[1] = ms;
+  return h->opt_retry ? nfail2 : 0;
+}
+
+// ---- host-buffer entry: stage through device buffers ------------------------------------
+static int h2d(gckpp_gpu_handle *h, DevBuf &b, const void *src, size_t bytes)
+{
+  if (b.ensure(bytes)) return fail(-1002, "out of device memory (%zu MB)", bytes >> 20);
+  CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin, double tout,
+                                   const double *conc_in, const double *rconst,
+                                   const double *temp, const double *numden, const double *h2o,
+                                   const double *photol, const double *khet,
+                                   const double *atol, const double *rtol,
+                                   const int32_t *icntrl, const double *rcntrl,
+                                   const double *hstart, const uint8_t *active,
+                                   double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+{
+  if (!h) return fail(-10, "NULL handle");
+  if (ncell < 0 || !conc_in || !conc_out) return fail(-10, "gckpp_gpu_integrate: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  int rc;
+  CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+  if ((rc = h2d(h, h->s_conc_in, conc_in, sizeof(double) * T->nspec * nc))) return rc;
+  if (rconst && (rc = h2d(h, h->s_rconst, rconst, sizeof(double) * T->nreact * nc))) return rc;
+  double *d_temp = nullptr, *d_numden = nullptr, *d_h2o = nullptr;
+  if (temp && numden && h2o) {
+    if (h->s_met.ensure(3 * sizeof(double) * nc)) return fail(-1002, "out of device memory");
+    d_temp = h->s_met.as<double>(); d_numden = d_temp + nc; d_h2o = d_numden + nc;
+    CUDA_TRY(cudaMemcpyAsync(d_temp, temp, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_numden, numden, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_h2o, h2o, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (photol && T->nphot && (rc = h2d(h, h->s_photol, photol, sizeof(double) * T->nphot * nc))) return rc;
+  if (khet && T->next && (rc = h2d(h, h->s_khet, khet, sizeof(double) * T->next * nc))) return rc;
+  if (hstart && (rc = h2d(h, h->s_hstart, hstart, sizeof(double) * nc))) return rc;
+  if (active && (rc = h2d(h, h->s_active, active, nc))) return rc;
+  if (h->s_conc_out.ensure(sizeof(double) * T->nspec * nc) || h->s_ist.ensure(sizeof(int) * 8 * nc) ||
+      h->s_rst.ensure(sizeof(double) * 4 * nc) || h->s_ierr.ensure(sizeof(int) * nc))
+    return fail(-1002, "out of device memory");
+  CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+  rc = gckpp_gpu_integrate_device(h, ncell, tin, tout, h->s_conc_in.as<double>(),
+                                  rconst ? h->s_rconst.as<double>() : nullptr, d_temp, d_numden, d_h2o,
+                                  (photol && T->nphot) ? h->s_photol.as<double>() : nullptr,
+                                  (khet && T->next) ? h->s_khet.as<double>() : nullptr, atol, rtol, icntrl, rcntrl,
+                                  hstart ? h->s_hstart.as<double>() : nullptr,
+                                  active ? h->s_active.as<uint8_t>() : nullptr, h->s_conc_out.as<double>(),
+                                  h->s_ist.as<int32_t>(), h->s_rst.as<double>(), h->s_ierr.as<int32_t>());
+  if (rc < 0) {
+    if (rc >= -5 && ierr) for (size_t i = 0; i < nc; i++) ierr[i] = rc;
+    return rc;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
+  CUDA_TRY(cudaMemcpyAsync(conc_out, h->s_conc_out.p, sizeof(double) * T->nspec * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (istatus) CUDA_TRY(cudaMemcpyAsync(istatus, h->s_ist.p, sizeof(int) * 8 * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (rstatus) CUDA_TRY(cudaMemcpyAsync(rstatus, h->s_rst.p, sizeof(double) * 4 * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (ierr) CUDA_TRY(cudaMemcpyAsync(ierr, h->s_ierr.p, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, h->ev[4], h->ev[5]);
+  cudaEventElapsedTime(&b, h->ev[6], h->ev[7]);
+  h->stats[2] = a + b;
+  return rc;
+}
+
+extern "C" int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *h, int ncell,
+                                              const double *temp, const double *numden, const double *h2o,
+                                              const double *photol, const double *khet, double *rconst_out)
+{
+  if (!h || !temp || !numden || !h2o || !rconst_out || ncell < 0) return fail(-10, "gckpp_gpu_update_rconst: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, rconst_out, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_update_rconst(gckpp_gpu_handle_t *h, int ncell,
+                                       const double *temp, const double *numden, const double *h2o,
+                                       const double *photol, const double *khet, double *rconst_out)
+{
+  if (!h || !temp || !numden || !h2o || !rconst_out || ncell < 0) return fail(-10, "gckpp_gpu_update_rconst: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  int rc;
+  if (h->s_met.ensure(3 * sizeof(double) * nc)) return fail(-1002, "out of device memory");
+  double *d_temp = h->s_met.as<double>(), *d_numden = d_temp + nc, *d_h2o = d_numden + nc;
+  CUDA_TRY(cudaMemcpyAsync(d_temp, temp, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_numden, numden, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_h2o, h2o, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+  if (photol && T->nphot && (rc = h2d(h, h->s_photol, photol, sizeof(double) * T->nphot * nc))) return rc;
+  if (khet && T->next && (rc = h2d(h, h->s_khet, khet, sizeof(double) * T->next * nc))) return rc;
+  if (h->s_rconst.ensure(sizeof(double) * T->nreact * nc)) return fail(-1002, "out of device memory");
+  CUDA_TRY(launch_update_rconst(h->mech_id, ncell, d_temp, d_numden, d_h2o,
+                                (photol && T->nphot) ? h->s_photol.as<double>() : nullptr,
+                                (khet && T->next) ? h->s_khet.as<double>() : nullptr, h->s_rconst.as<double>(), h->stream));
+  CUDA_TRY(cudaMemcpyAsync(rconst_out, h->s_rconst.p, sizeof(double) * T->nreact * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_fun(gckpp_gpu_handle_t *h, int ncell, const double *conc, const double *rconst,
+                             double *vdot, double *aout)
+{
+  if (!h || !conc || !rconst || ncell < 0) return fail(-10, "gckpp_gpu_fun: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, sizeof(double) * T->nspec * nc))) return rc;
+  if ((rc = h2d(h, h->s_rconst, rconst, sizeof(double) * T->nreact * nc))) return rc;
+  if (h->s_conc_out.ensure(sizeof(double) * T->nspec * nc) || h->scratch.ensure(sizeof(double) * T->nreact * nc))
+    return fail(-1002, "out of device memory");
+  CUDA_TRY(launch_fun_cells(h->M, ncell, h->s_conc_in.as<double>(), h->s_rconst.as<double>(),
+                            h->s_conc_out.as<double>(), h->scratch.as<double>(), h->stream));
+  if (vdot) CUDA_TRY(cudaMemcpyAsync(vdot, h->s_conc_out.p, sizeof(double) * T->nvar * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (aout) CUDA_TRY(cudaMemcpyAsync(aout, h->scratch.p, sizeof(double) * T->nreact * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_jac(gckpp_gpu_handle_t *h, int ncell, const double *conc, const double *rconst, double *jvs)
+{
+  if (!h || !conc || !rconst || !jvs || ncell < 0) return fail(-10, "gckpp_gpu_jac: bad arguments");
+  if (h->T->nnz == 0) return fail(-11, "mechanism has no Jacobian");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, sizeof(double) * T->nspec * nc))) return rc;
+  if ((rc = h2d(h, h->s_rconst, rconst, sizeof(double) * T->nreact * nc))) return rc;
+  if (h->scratch.ensure(sizeof(double) * ((size_t)T->nb + T->nnz) * nc)) return fail(-1002, "out of device memory");
+  double *B = h->scratch.as<double>(), *J = B + (size_t)T->nb * nc;
+  CUDA_TRY(launch_jac_cells(h->M, ncell, h->s_conc_in.as<double>(), h->s_rconst.as<double>(), B, J, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(jvs, J, sizeof(double) * T->nnz * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_decomp(gckpp_gpu_handle_t *h, int ncell, double *jvs, int32_t *ier)
+{
+  if (!h || !jvs || !ier || ncell < 0) return fail(-10, "gckpp_gpu_decomp: bad arguments");
+  if (h->T->nnz == 0) return fail(-11, "mechanism has no Jacobian");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  if (h->scratch.ensure(sizeof(double) * ((size_t)T->nvar + T->nnz) * nc + sizeof(int) * nc)) return fail(-1002, "out of device memory");
+  double *J = h->scratch.as<double>(), *W = J + (size_t)T->nnz * nc;
+  int *E = (int *)(W + (size_t)T->nvar * nc);
+  CUDA_TRY(cudaMemcpyAsync(J, jvs, sizeof(double) * T->nnz * nc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_decomp_cells(h->M, ncell, J, W, E, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(jvs, J, sizeof(double) * T->nnz * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(ier, E, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_solve(gckpp_gpu_handle_t *h, int ncell, const double *jvs, double *x)
+{
+  if (!h || !jvs || !x || ncell < 0) return fail(-10, "gckpp_gpu_solve: bad arguments");
+  if (h->T->nnz == 0) return fail(-11, "mechanism has no Jacobian");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  if (h->scratch.ensure(sizeof(double) * ((size_t)T->nvar + T->nnz) * nc)) return fail(-1002, "out of device memory");
+  double *J = h->scratch.as<double>(), *X = J + (size_t)T->nnz * nc;
+  CUDA_TRY(cudaMemcpyAsync(J, jvs, sizeof(double) * T->nnz * nc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(X, x, sizeof(double) * T->nvar * nc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_solve_cells(h->M, ncell, J, X, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(x, X, sizeof(double) * T->nvar * nc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_last_stats(gckpp_gpu_handle_t *h, double *stats)
+{
+  if (!h || !stats) return fail(-10, "gckpp_gpu_last_stats: NULL argument");
+  for (int i = 0; i < 16; i++) stats[i] = h->stats[i];
+  return 0;
+}

@@ -1,0 +1,25 @@
+// Kernel launchers (one translation unit per kernel family, see the build recipe).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include "ros_common.cuh"
+
+// ros_generic.cu (compiled with -fmad=false)
+cudaError_t launch_ros_generic(const MechDev &M, const RosArgs &a, int blocks, int threads, cudaStream_t s);
+cudaError_t launch_feuler(const MechDev &M, const RosArgs &a, int icntrl16, cudaStream_t s);
+cudaError_t launch_fun_cells(const MechDev &M, int ncell, const double *conc, const double *rconst,
+                             double *vdot, double *aout, cudaStream_t s);
+cudaError_t launch_jac_cells(const MechDev &M, int ncell, const double *conc, const double *rconst,
+                             double *bwork, double *jvs, cudaStream_t s);
+cudaError_t launch_decomp_cells(const MechDev &M, int ncell, double *jvs, double *wwork, int *ier, cudaStream_t s);
+cudaError_t launch_solve_cells(const MechDev &M, int ncell, const double *jvs, double *x, cudaStream_t s);
+
+// kernels_misc.cu
+cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
+                                 const double *h2o, const double *photol, const double *khet,
+                                 double *rconst, cudaStream_t s);
+cudaError_t launch_fill_int(int *p, int n, int v, cudaStream_t s);
+cudaError_t launch_select_active(int ncell, const uint8_t *active, int nspec, const double *conc_in,
+                                 double *conc_out, int *istatus, double *rstatus, int *ierr,
+                                 int *cell_list, int *count, cudaStream_t s);
+cudaError_t launch_select_failed(int ncell, const int *ierr, int *cell_list, int *count, cudaStream_t s);

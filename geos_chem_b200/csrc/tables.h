@@ -1,0 +1,37 @@
+// Mechanism tables shared by the host (static data emitted by kppgen/emit_cuda.py) and the
+// table-driven kernels.  Term encoding: see emit_cuda.py.
+#pragma once
+#include <stdint.h>
+
+struct gckpp_host_tables_t {
+  const char *name;
+  int nvar, nfix, nspec, nreact, nnz, nb, nphot, next, fun_split;
+  const int *a_term;                                   // [nreact][4]
+  const int *p_ptr; const double *p_coef; const int *p_rxn; int np;   // production  (Fun_SPLIT P_VAR)
+  const int *d_ptr; const int *d_term; int nd;         // destruction (Fun_SPLIT D_VAR) [nd][4]
+  const int *v_ptr; const double *v_coef; const int *v_rxn; int nv;   // aggregate Fun Vdot
+  const int *crow, *diag, *icol;                       // CSR of LU_CROW/LU_DIAG/LU_ICOL (0-based)
+  const int *b_term;                                   // [nb][4]   Jac_SP partials
+  const int *j_ptr; const double *j_coef; const int *j_b; int nj;     // JVS sums
+  const double *lit; int nlit;
+};
+
+// Device copy: same fields, device pointers.
+struct MechDev {
+  int nvar, nfix, nspec, nreact, nnz, nb, nphot, next, fun_split;
+  const int4 *a_term;
+  const int *p_ptr; const double *p_coef; const int *p_rxn;
+  const int *d_ptr; const int4 *d_term;
+  const int *v_ptr; const double *v_coef; const int *v_rxn;
+  const int *crow, *diag, *icol;
+  const int4 *b_term;
+  const int *j_ptr; const double *j_coef; const int *j_b;
+  const double *lit;
+};
+
+// Per-cell meteorological scalars (commonIncludeVars.H) as Set_Kpp_GridBox_Values derives them
+// (GeosCore/fullchem_mod.F90:2139-2150).
+struct MetCell {
+  double TEMP, NUMDEN, H2O;
+  double INV_TEMP, TEMP_OVER_K300, K300_OVER_TEMP, SR_TEMP;
+};

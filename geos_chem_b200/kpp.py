@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's KPP interface over the C ABI (include/gckpp_gpu.h).
+
+Names and argument meaning follow the reference so callers (and the parity tests) read like
+the Fortran they replace:
+
+  Update_RCONST   KPP/<mech>/gckpp_Rates.F90:408
+  Integrate       KPP/<mech>/gckpp_Integrator.F90:80      (TIN, TOUT, ICNTRL_U, RCNTRL_U -> ISTATUS, RSTATUS, IERR)
+  Fun             KPP/<mech>/gckpp_Function.F90:51         (V, F, RCT -> Vdot, Aout)
+  Jac_SP / KppDecomp / KppSolve   gckpp_Jacobian.F90:48, gckpp_LinearAlgebra.F90:46, :644
+
+The module variables the Fortran passes implicitly (C, RCONST, TEMP, NUMDEN, H2O, PHOTOL, ATOL,
+RTOL) are explicit arrays over cells here, CELL-FASTEST ([k, ncell], C-contiguous).
+numpy arrays go through the host entry points (copies inside the call); torch CUDA tensors
+go through the *_device entry points (no copies).  There is no CPU implementation: if the
+CUDA library is missing or no GPU is present, construction fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgckpp_b200.so")
+MECH_ID = {"fullchem": 0, "Hg": 1, "carbon": 2}
+
+# ISTATUS / RSTATUS slots (gckpp_Integrator.F90:57-63)
+Nfun, Njac, Nstp, Nacc, Nrej, Ndec, Nsol, Nsng = range(8)
+Ntexit, Nhexit, Nhnew, NARthr = range(4)
+
+_lib = None
+
+
+class KppError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libgckpp_b200.so and declare the C ABI. Raises if the library was not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise KppError("%s not found: build it with `python -m geos_chem_b200.build` "
+                       "(__graft_entry__.build()); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.gckpp_gpu_dims.argtypes = [C.c_int, ip]
+    L.gckpp_gpu_spc_name.argtypes = [C.c_int, C.c_int]
+    L.gckpp_gpu_spc_name.restype = C.c_char_p
+    L.gckpp_gpu_init.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.gckpp_gpu_finalize.argtypes = [vp]
+    L.gckpp_gpu_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    sig = [vp, C.c_int, C.c_double, C.c_double] + [vp] * 17
+    L.gckpp_gpu_integrate.argtypes = sig
+    L.gckpp_gpu_integrate_device.argtypes = sig
+    L.gckpp_gpu_update_rconst.argtypes = [vp, C.c_int] + [vp] * 6
+    L.gckpp_gpu_update_rconst_device.argtypes = [vp, C.c_int] + [vp] * 6
+    L.gckpp_gpu_fun.argtypes = [vp, C.c_int] + [vp] * 4
+    L.gckpp_gpu_jac.argtypes = [vp, C.c_int] + [vp] * 3
+    L.gckpp_gpu_decomp.argtypes = [vp, C.c_int] + [vp] * 2
+    L.gckpp_gpu_solve.argtypes = [vp, C.c_int] + [vp] * 2
+    L.gckpp_gpu_last_stats.argtypes = [vp, dp]
+    L.gckpp_gpu_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_finalize", "gckpp_gpu_set_option",
+           "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
+           "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
+           "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error"]
+
+
+def mech_dims(mech):
+    L = load_library()
+    d = (C.c_int32 * 7)()
+    if L.gckpp_gpu_dims(MECH_ID[mech], d) != 0:
+        raise KppError(L.gckpp_gpu_last_error().decode())
+    return dict(zip(("nvar", "nfix", "nspec", "nreact", "lu_nonzero", "nphot", "next"), (int(x) for x in d)))
+
+
+def spc_names(mech):
+    L = load_library()
+    n = mech_dims(mech)["nspec"]
+    return [L.gckpp_gpu_spc_name(MECH_ID[mech], i).decode() for i in range(n)]
+
+
+def _is_torch(x):
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _np(x, dtype, shape=None, name="array"):
+    if x is None:
+        return None
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(a.shape)))
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class KppSolver:
+    """One solver instance = one mechanism on one GPU (gckpp_gpu_init ... gckpp_gpu_finalize)."""
+
+    def __init__(self, mech="fullchem", device=0, max_cells=1 << 20, retry=False):
+        self.L = load_library()
+        self.mech = mech
+        self.dims = mech_dims(mech)
+        self.device = device
+        h = C.c_void_p()
+        rc = self.L.gckpp_gpu_init(MECH_ID[mech], device, max_cells, C.byref(h))
+        if rc != 0:
+            raise KppError("gckpp_gpu_init failed (%d): %s" % (rc, self.L.gckpp_gpu_last_error().decode()))
+        self.h = h
+        if retry:
+            self.set_option("retry", 1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gckpp_gpu_finalize(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_option(self, key, value):
+        rc = self.L.gckpp_gpu_set_option(self.h, key.encode(), int(value))
+        if rc != 0:
+            raise KppError(self.L.gckpp_gpu_last_error().decode())
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise KppError("%s failed (%d): %s" % (what, rc, self.L.gckpp_gpu_last_error().decode()))
+        return rc
+
+    # ------------------------------------------------------------------ Update_RCONST
+    def Update_RCONST(self, TEMP, NUMDEN, H2O, PHOTOL=None, khet=None, out=None):
+        """RCONST[NREACT, ncell] from per-cell TEMP, NUMDEN, H2O [ncell], PHOTOL [NPHOT, ncell] and the
+        externally supplied constants khet [NEXT, ncell] (K_MT, K_CLD, State_Het laws)."""
+        d = self.dims
+        if _is_torch(TEMP):
+            import torch
+            ncell = TEMP.shape[0]
+            if out is None:
+                out = torch.empty((d["nreact"], ncell), dtype=torch.float64, device=TEMP.device)
+            rc = self.L.gckpp_gpu_update_rconst_device(self.h, ncell, _ptr(TEMP), _ptr(NUMDEN), _ptr(H2O),
+                                                       _ptr(PHOTOL), _ptr(khet), _ptr(out))
+            self._check(rc, "Update_RCONST")
+            return out
+        TEMP = _np(TEMP, np.float64)
+        ncell = TEMP.shape[0]
+        NUMDEN = _np(NUMDEN, np.float64, (ncell,), "NUMDEN")
+        H2O = _np(H2O, np.float64, (ncell,), "H2O")
+        PHOTOL = _np(PHOTOL, np.float64, (d["nphot"], ncell), "PHOTOL")
+        khet = _np(khet, np.float64, (d["next"], ncell), "khet")
+        out = np.empty((d["nreact"], ncell), np.float64)
+        rc = self.L.gckpp_gpu_update_rconst(self.h, ncell, _ptr(TEMP), _ptr(NUMDEN), _ptr(H2O), _ptr(PHOTOL),
+                                            _ptr(khet), _ptr(out))
+        self._check(rc, "Update_RCONST")
+        return out
+
+    # ------------------------------------------------------------------ Integrate
+    def Integrate(self, TIN, TOUT, C_in, RCONST=None, ATOL=None, RTOL=None, ICNTRL_U=None, RCNTRL_U=None,
+                  hstart=None, active=None, TEMP=None, NUMDEN=None, H2O=None, PHOTOL=None, khet=None,
+                  C_out=None, ISTATUS=None, RSTATUS=None, IERR=None):
+        """Batched Integrate.  C_in [NSPEC, ncell]; RCONST [NREACT, ncell] or None (then TEMP, NUMDEN,
+        H2O [, PHOTOL, khet] are required and Update_RCONST runs on the device first).
+        Returns (C_out, ISTATUS[8, ncell], RSTATUS[4, ncell], IERR[ncell], n_failed_twice)."""
+        d = self.dims
+        ic = _np(ICNTRL_U if ICNTRL_U is not None else np.zeros(20), np.int32, (20,), "ICNTRL_U")
+        rcn = _np(RCNTRL_U if RCNTRL_U is not None else np.zeros(20), np.float64, (20,), "RCNTRL_U")
+        at = _np(ATOL, np.float64, (d["nvar"],), "ATOL")
+        rt = _np(RTOL, np.float64, (d["nvar"],), "RTOL")
+        if _is_torch(C_in):
+            import torch
+            ncell = C_in.shape[1]
+            dev = C_in.device
+            assert C_in.dtype == torch.float64 and C_in.is_contiguous()
+            if C_out is None:
+                C_out = torch.empty_like(C_in)
+            if ISTATUS is None:
+                ISTATUS = torch.empty((8, ncell), dtype=torch.int32, device=dev)
+            if RSTATUS is None:
+                RSTATUS = torch.empty((4, ncell), dtype=torch.float64, device=dev)
+            if IERR is None:
+                IERR = torch.empty((ncell,), dtype=torch.int32, device=dev)
+            fn = self.L.gckpp_gpu_integrate_device
+        else:
+            C_in = _np(C_in, np.float64)
+            if C_in.ndim != 2 or C_in.shape[0] != d["nspec"]:
+                raise ValueError("C_in: expected [%d, ncell], got %s" % (d["nspec"], C_in.shape))
+            ncell = C_in.shape[1]
+            RCONST = _np(RCONST, np.float64, (d["nreact"], ncell), "RCONST")
+            TEMP = _np(TEMP, np.float64, (ncell,), "TEMP")
+            NUMDEN = _np(NUMDEN, np.float64, (ncell,), "NUMDEN")
+            H2O = _np(H2O, np.float64, (ncell,), "H2O")
+            PHOTOL = _np(PHOTOL, np.float64, (d["nphot"], ncell), "PHOTOL")
+            khet = _np(khet, np.float64, (d["next"], ncell), "khet")
+            hstart = _np(hstart, np.float64, (ncell,), "hstart")
+            active = _np(active, np.uint8, (ncell,), "active")
+            C_out = np.empty_like(C_in)
+            ISTATUS = np.zeros((8, ncell), np.int32)
+            RSTATUS = np.zeros((4, ncell), np.float64)
+            IERR = np.zeros((ncell,), np.int32)
+            fn = self.L.gckpp_gpu_integrate
+        rc = fn(self.h, ncell, float(TIN), float(TOUT), _ptr(C_in), _ptr(RCONST), _ptr(TEMP), _ptr(NUMDEN),
+                _ptr(H2O), _ptr(PHOTOL), _ptr(khet), _ptr(at), _ptr(rt), _ptr(ic), _ptr(rcn), _ptr(hstart),
+                _ptr(active), _ptr(C_out), _ptr(ISTATUS), _ptr(RSTATUS), _ptr(IERR))
+        if rc < 0 and rc >= -5:
+            # option errors are per-call in the reference too: every cell reports the same IERR
+            return C_out, ISTATUS, RSTATUS, IERR, rc
+        self._check(rc, "Integrate")
+        return C_out, ISTATUS, RSTATUS, IERR, rc
+
+    # ------------------------------------------------------------------ diagnostics / pieces (host arrays)
+    def Fun(self, C_in, RCONST):
+        d = self.dims
+        C_in = _np(C_in, np.float64)
+        ncell = C_in.shape[1]
+        RCONST = _np(RCONST, np.float64, (d["nreact"], ncell), "RCONST")
+        vdot = np.empty((d["nvar"], ncell), np.float64)
+        aout = np.empty((d["nreact"], ncell), np.float64)
+        self._check(self.L.gckpp_gpu_fun(self.h, ncell, _ptr(C_in), _ptr(RCONST), _ptr(vdot), _ptr(aout)), "Fun")
+        return vdot, aout
+
+    def Jac_SP(self, C_in, RCONST):
+        d = self.dims
+        C_in = _np(C_in, np.float64)
+        ncell = C_in.shape[1]
+        RCONST = _np(RCONST, np.float64, (d["nreact"], ncell), "RCONST")
+        jvs = np.empty((d["lu_nonzero"], ncell), np.float64)
+        self._check(self.L.gckpp_gpu_jac(self.h, ncell, _ptr(C_in), _ptr(RCONST), _ptr(jvs)), "Jac_SP")
+        return jvs
+
+    def KppDecomp(self, JVS):
+        d = self.dims
+        j = _np(JVS, np.float64).copy()
+        ncell = j.shape[1]
+        ier = np.zeros(ncell, np.int32)
+        self._check(self.L.gckpp_gpu_decomp(self.h, ncell, _ptr(j), _ptr(ier)), "KppDecomp")
+        return j, ier
+
+    def KppSolve(self, JVS, X):
+        j = _np(JVS, np.float64)
+        x = _np(X, np.float64).copy()
+        self._check(self.L.gckpp_gpu_solve(self.h, j.shape[1], _ptr(j), _ptr(x)), "KppSolve")
+        return x
+
+    def last_stats(self):
+        s = (C.c_double * 16)()
+        self.L.gckpp_gpu_last_stats(self.h, s)
+        keys = ("integrate_ms", "rconst_ms", "copy_ms", "cells", "retried", "failed_twice", "launches", "sum_nstp", "sum_nacc")
+        return dict(zip(keys, (float(x) for x in s)))

@@ -1,0 +1,141 @@
+/* gckpp_gpu.h -- C ABI of the B200 KPP chemistry path (libgckpp_b200.so).
+ *
+ * Drop-in, batched replacement for what GEOS-Chem's chemistry drivers call per grid box:
+ *
+ *   Update_RCONST()                         KPP/<mech>/gckpp_Rates.F90:408
+ *   Integrate(TIN,TOUT,ICNTRL_U,RCNTRL_U,   KPP/<mech>/gckpp_Integrator.F90:80-81
+ *             ISTATUS_U,RSTATUS_U,IERR_U)
+ *   Fun(V,F,RCT,Vdot,Aout)                  KPP/<mech>/gckpp_Function.F90:51
+ *
+ * called from Do_FullChem (GeosCore/fullchem_mod.F90:953,1033,1157,1162), ChemMercury
+ * (GeosCore/mercury_mod.F90:1106,1132) and Chem_Carbon_Gases (GeosCore/carbon_gases_mod.F90:532,539).
+ * The reference passes state through OpenMP-threadprivate module variables (C, RCONST, TEMP,
+ * NUMDEN, H2O, PHOTOL, K_MT, K_CLD, ATOL, RTOL: gckpp_Global.F90:47-80); here the same
+ * quantities are arrays over cells.  One call covers a whole chemistry step on one GPU.
+ *
+ * Conventions
+ *   - ISO_C_BINDING compatible: scalars by value, arrays as raw pointers, no descriptors.
+ *   - Every per-cell array is CELL-FASTEST: element (k, cell) at  a[k*ncell + cell] .  This is
+ *     the memory order of the 356 separate State_Chm%Species(n)%Conc(I,J,L) arrays with
+ *     cell = I + NX*(J-1) + NX*NY*(L-1)  (0-based here).
+ *   - Species order = the mechanism's SPC_NAMES (variable species first, then fixed).
+ *   - The caller owns every array passed in; nothing is retained after return.
+ *   - Return value: 0 ok; >0 = number of cells that failed twice (retry enabled);
+ *     <0 = -(1000 + cudaError) for CUDA errors, -1..-5 option errors (same codes as the
+ *     reference's IERR), -10 bad argument, -11 library built without the requested mechanism.
+ *   - Per-cell ierr[] uses the reference's codes (gckpp_Integrator.F90:551-571): 1 success,
+ *     -6 too many steps, -7 step too small, -8 matrix repeatedly singular; 0 = cell not in
+ *     the chemistry grid (active[cell]==0).
+ *   - ICNTRL/RCNTRL have the reference's meaning (gckpp_Integrator.F90:165-260): zero /
+ *     non-positive entries mean "default" (Integrate's WHERE merge, :112-117).  ICNTRL(15)
+ *     must be -1 (rates are never refreshed inside the integrator, as in GEOS-Chem).
+ */
+#ifndef GCKPP_GPU_H
+#define GCKPP_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCKPP_MECH_FULLCHEM 0
+#define GCKPP_MECH_HG       1
+#define GCKPP_MECH_CARBON   2
+
+typedef struct gckpp_gpu_handle gckpp_gpu_handle_t;
+
+/* dims[0..6] = NVAR, NFIX, NSPEC, NREACT, LU_NONZERO, NPHOT (PHOTOL entries read), NEXT
+ * (rate constants supplied by the caller: K_MT, K_CLD and the State_Het-dependent laws, in
+ * ascending reaction order; fullchem: 113).  (gckpp_Parameters.F90:34-54) */
+int gckpp_gpu_dims(int mech_id, int32_t *dims);
+
+/* Species name of index i (0-based; gckpp_Monitor.F90 SPC_NAMES); NULL if out of range. */
+const char *gckpp_gpu_spc_name(int mech_id, int i);
+
+/* Create a solver instance on CUDA device `device`, sized for up to max_cells per call
+ * (larger calls are processed in waves).  Replaces nothing in the reference (KPP has no
+ * state beyond its module variables); owns device buffers and a stream. */
+int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_handle_t **handle);
+int gckpp_gpu_finalize(gckpp_gpu_handle_t *handle);
+
+/* Options (integer-valued):
+ *   "retry"      1 = on IERR<0 redo the cell once with Hstart=0 from the saved
+ *                concentrations (Do_FullChem's policy, fullchem_mod.F90:1138-1162); default 0
+ *   "kernel"     0 = table-driven kernels, 1 = mechanism-specialised kernels (default: best available)
+ *   "sort"       1 = visit cells in descending previous-step cost (hstart ascending); default 0
+ */
+int gckpp_gpu_set_option(gckpp_gpu_handle_t *handle, const char *key, int value);
+
+/* Update_RCONST + Integrate for ncell cells.  HOST pointers; copies in/out internally.
+ *   conc_in   [NSPEC][ncell]  concentrations, molec/cm3            (C of gckpp_Global)
+ *   rconst    [NREACT][ncell] rate constants, or NULL to compute them on the device from
+ *             temp/numden/h2o/photol/khet (Update_RCONST)
+ *   temp,numden,h2o [ncell]   TEMP [K], NUMDEN [molec/cm3], H2O [molec/cm3]
+ *                             (Set_Kpp_GridBox_Values, fullchem_mod.F90:2139-2141)
+ *   photol    [NPHOT][ncell]  PHOTOL(1:NPHOT) J-values [1/s]  (fullchem_mod.F90:621-642)
+ *   khet      [NEXT][ncell]   externally supplied rate constants (see gckpp_gpu_dims)
+ *   atol,rtol [NVAR]          shared tolerances (gckpp_Global.F90:78-80)
+ *   icntrl[20], rcntrl[20]    integrator options
+ *   hstart    [ncell] or NULL per-cell RCNTRL(3) = State_Chm%KPPHvalue (fullchem_AutoReduceFuncs.F90:287)
+ *   active    [ncell] or NULL 0 = skip cell (not InChemGrid, fullchem_mod.F90:804)
+ *   conc_out  [NSPEC][ncell]  raw integrator output (no MAX(C,0) clip: fullchem_mod.F90:1345 is the caller's)
+ *   istatus   [8][ncell]      Nfun,Njac,Nstp,Nacc,Nrej,Ndec,Nsol,Nsng   (may be NULL)
+ *   rstatus   [4][ncell]      Texit,Hexit,Hnew,ARthr                    (may be NULL)
+ *   ierr      [ncell]                                                    (may be NULL)
+ */
+int gckpp_gpu_integrate(gckpp_gpu_handle_t *handle, int ncell, double tin, double tout,
+                        const double *conc_in, const double *rconst,
+                        const double *temp, const double *numden, const double *h2o,
+                        const double *photol, const double *khet,
+                        const double *atol, const double *rtol,
+                        const int32_t *icntrl, const double *rcntrl,
+                        const double *hstart, const uint8_t *active,
+                        double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr);
+
+/* Same, with every per-cell array already resident in device memory (atol/rtol/icntrl/rcntrl
+ * stay host pointers).  Asynchronous work is ordered on the handle's stream and the call
+ * returns after the stream is synchronised.  rconst_work: optional device scratch
+ * [NREACT][ncell] used when rconst == NULL (NULL = library allocates). */
+int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *handle, int ncell, double tin, double tout,
+                               const double *conc_in, const double *rconst,
+                               const double *temp, const double *numden, const double *h2o,
+                               const double *photol, const double *khet,
+                               const double *atol, const double *rtol,
+                               const int32_t *icntrl, const double *rcntrl,
+                               const double *hstart, const uint8_t *active,
+                               double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr);
+
+/* Update_RCONST alone (RxnConst diagnostic, fullchem_mod.F90:997-1002): rconst_out [NREACT][ncell]. */
+int gckpp_gpu_update_rconst(gckpp_gpu_handle_t *handle, int ncell,
+                            const double *temp, const double *numden, const double *h2o,
+                            const double *photol, const double *khet, double *rconst_out);
+int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *handle, int ncell,
+                                   const double *temp, const double *numden, const double *h2o,
+                                   const double *photol, const double *khet, double *rconst_out);
+
+/* Fun(V,F,RCT,Vdot,Aout) over cells (RxnRate diagnostics, fullchem_mod.F90:967-992):
+ * vdot [NVAR][ncell] and aout [NREACT][ncell]; either output may be NULL.  Host pointers. */
+int gckpp_gpu_fun(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst,
+                  double *vdot, double *aout);
+
+/* Pieces exposed for parity tests (host pointers, cell-fastest):
+ *   jac:    Jac_SP  -> jvs [LU_NONZERO][ncell]
+ *   decomp: KppDecomp in place on jvs; ier[ncell] = 0 or the 1-based singular row
+ *   solve:  KppSolve in place on x [NVAR][ncell] */
+int gckpp_gpu_jac(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst, double *jvs);
+int gckpp_gpu_decomp(gckpp_gpu_handle_t *handle, int ncell, double *jvs, int32_t *ier);
+int gckpp_gpu_solve(gckpp_gpu_handle_t *handle, int ncell, const double *jvs, double *x);
+
+/* Statistics of the last integrate call on this handle:
+ * stats[0] kernel time of the integrator [ms] (CUDA events on the handle's stream),
+ * stats[1] kernel time of Update_RCONST [ms], stats[2] H2D+D2H time [ms] (host entry only),
+ * stats[3] cells integrated, stats[4] cells retried, stats[5] cells failed twice,
+ * stats[6] kernels launched, stats[7] sum of Nstp, stats[8] sum of Nacc. */
+int gckpp_gpu_last_stats(gckpp_gpu_handle_t *handle, double *stats /* [16] */);
+
+/* Last error text (thread-local). */
+const char *gckpp_gpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
