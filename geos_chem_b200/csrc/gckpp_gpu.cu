@@ -72,11 +72,11 @@ struct gckpp_gpu_handle {
   const gckpp_host_tables_t *T = nullptr;
   MechDev M{};
   std::vector<void *> table_allocs;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev[8]{};
   int sm_count = 0;
   // integrator launch geometry + workspace
-  int threads = 128, blocks_per_sm = 2, max_blocks = 0;
+  int threads = 128, blocks_per_sm = 5, max_blocks = 0;
   WsLayout L{};
   DevBuf work, next, sums, tol, cell_list, counter, rconst_work, scratch;
   // staging for the host entry points
@@ -151,7 +151,8 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
   for (auto &e : h->ev) CUDA_TRY(cudaEventCreate(&e));
   MechDev &M = h->M;
   M.nvar = T->nvar; M.nfix = T->nfix; M.nspec = T->nspec; M.nreact = T->nreact; M.nnz = T->nnz;
@@ -190,8 +191,26 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_set_stream(gckpp_gpu_handle_t *h, void *cuda_stream)
+{
+  if (!h) return fail(-10, "NULL handle");
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_fp64_peak(int device, double *tflops_out, double *ms_out)
+{
+  if (!tflops_out) return fail(-10, "NULL argument");
+  CUDA_TRY(cudaSetDevice(device));
+  double tf = 0, ms = 0;
+  CUDA_TRY(measure_fp64_peak(&tf, &ms));
+  *tflops_out = tf;
+  if (ms_out) *ms_out = ms;
   return 0;
 }
 
@@ -471,6 +490,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->stats[0] = ms;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->stats[1] = ms;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->stats[9] = ms;
   return h->opt_retry ? nfail2 : 0;
 }
 

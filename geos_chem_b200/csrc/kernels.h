@@ -23,3 +23,4 @@ cudaError_t launch_select_active(int ncell, const uint8_t *active, int nspec, co
                                  double *conc_out, int *istatus, double *rstatus, int *ierr,
                                  int *cell_list, int *count, cudaStream_t s);
 cudaError_t launch_select_failed(int ncell, const int *ierr, int *cell_list, int *count, cudaStream_t s);
+cudaError_t measure_fp64_peak(double *tflops, double *ms);

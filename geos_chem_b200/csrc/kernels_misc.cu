@@ -71,7 +71,50 @@ __global__ void select_failed_kernel(int ncell, const int *__restrict__ ierr, in
   if (cell < ncell && ierr[cell] < 0) cell_list[atomicAdd(count, 1)] = cell;
 }
 
+// FP64 FMA peak: 8 independent DFMA chains per thread, 4096 iterations, 8 CTAs of 256 per SM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, double a, double b, int iters)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;   // never true: keeps the chains alive
+}
+
 }  // namespace
+
+cudaError_t measure_fp64_peak(double *tflops, double *ms_out)
+{
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+  fp64_peak_kernel<<<blocks, threads>>>(d, 0.999999, 1e-9, 256);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(a);
+    fp64_peak_kernel<<<blocks, threads>>>(d, 0.999999, 1e-9, iters);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  e = cudaGetLastError();
+  double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  *ms_out = best;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(d);
+  return e;
+}
 
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,

@@ -67,8 +67,8 @@ def _normal(seed, cell, k, stream):
 
 def rate_layout(mech="fullchem"):
     """(gas, phot[(r,k)], ext, null, nphot) index lists of Update_RCONST for a mechanism"""
-    from .kppgen import ir, emit_c
-    return emit_c.rate_layout(ir.load(mech))
+    from .kppgen import ir, rates
+    return rates.rate_layout(ir.load(mech))
 
 
 def fixture_inputs(fx, mech="fullchem"):

@@ -61,6 +61,8 @@ def load_library(path=None):
     L.gckpp_gpu_decomp.argtypes = [vp, C.c_int] + [vp] * 2
     L.gckpp_gpu_solve.argtypes = [vp, C.c_int] + [vp] * 2
     L.gckpp_gpu_last_stats.argtypes = [vp, dp]
+    L.gckpp_gpu_set_stream.argtypes = [vp, vp]
+    L.gckpp_gpu_fp64_peak.argtypes = [C.c_int, dp, dp]
     L.gckpp_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -69,7 +71,8 @@ def load_library(path=None):
 EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_finalize", "gckpp_gpu_set_option",
            "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
            "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
-           "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error"]
+           "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error", "gckpp_gpu_set_stream",
+           "gckpp_gpu_fp64_peak"]
 
 
 def mech_dims(mech):
@@ -134,6 +137,10 @@ class KppSolver:
         rc = self.L.gckpp_gpu_set_option(self.h, key.encode(), int(value))
         if rc != 0:
             raise KppError(self.L.gckpp_gpu_last_error().decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        """run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream"""
+        self.L.gckpp_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None)
 
     def _check(self, rc, what):
         if rc < 0:
@@ -256,5 +263,16 @@ class KppSolver:
     def last_stats(self):
         s = (C.c_double * 16)()
         self.L.gckpp_gpu_last_stats(self.h, s)
-        keys = ("integrate_ms", "rconst_ms", "copy_ms", "cells", "retried", "failed_twice", "launches", "sum_nstp", "sum_nacc")
+        keys = ("integrate_ms", "rconst_ms", "copy_ms", "cells", "retried", "failed_twice", "launches", "sum_nstp",
+                "sum_nacc", "device_ms")
         return dict(zip(keys, (float(x) for x in s)))
+
+
+def fp64_peak(device=0):
+    """measured FP64 FMA peak of the device [TFLOP/s] (register-resident DFMA chains on every SM)"""
+    L = load_library()
+    tf, ms = C.c_double(), C.c_double()
+    rc = L.gckpp_gpu_fp64_peak(device, C.byref(tf), C.byref(ms))
+    if rc != 0:
+        raise KppError(L.gckpp_gpu_last_error().decode())
+    return tf.value

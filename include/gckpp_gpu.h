@@ -125,11 +125,22 @@ int gckpp_gpu_jac(gckpp_gpu_handle_t *handle, int ncell, const double *conc, con
 int gckpp_gpu_decomp(gckpp_gpu_handle_t *handle, int ncell, double *jvs, int32_t *ier);
 int gckpp_gpu_solve(gckpp_gpu_handle_t *handle, int ncell, const double *jvs, double *x);
 
+/* Run this handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
+ * restores the handle's own stream).  Lets the host order the call against its own transfers
+ * and time it with its own events. */
+int gckpp_gpu_set_stream(gckpp_gpu_handle_t *handle, void *cuda_stream);
+
+/* Measure the device's FP64 FMA peak [TFLOP/s] with a register-resident DFMA chain kernel on
+ * every SM (the non-tensor FP64 pipe is the compute roofline of this path; MEASURED_PEAKS.json
+ * only holds HBM and BF16).  ms_out (may be NULL) receives the kernel time. */
+int gckpp_gpu_fp64_peak(int device, double *tflops_out, double *ms_out);
+
 /* Statistics of the last integrate call on this handle:
  * stats[0] kernel time of the integrator [ms] (CUDA events on the handle's stream),
  * stats[1] kernel time of Update_RCONST [ms], stats[2] H2D+D2H time [ms] (host entry only),
  * stats[3] cells integrated, stats[4] cells retried, stats[5] cells failed twice,
- * stats[6] kernels launched, stats[7] sum of Nstp, stats[8] sum of Nacc. */
+ * stats[6] kernels launched, stats[7] sum of Nstp, stats[8] sum of Nacc,
+ * stats[9] device time of the whole call (rate constants + integration + retry) [ms]. */
 int gckpp_gpu_last_stats(gckpp_gpu_handle_t *handle, double *stats /* [16] */);
 
 /* Last error text (thread-local). */

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/gckpp_gpu.h declares (no compute calls:
+this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+from geos_chem_b200 import kpp
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "gckpp_gpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gckpp_gpu_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libgckpp_b200.so does not export %s" % s
+    assert sorted(kpp.EXPORTS) == syms
+
+
+def test_dims_and_names_without_gpu(lib):
+    d = kpp.mech_dims("fullchem")
+    assert (d["nvar"], d["nfix"], d["nspec"], d["nreact"], d["lu_nonzero"]) == (353, 3, 356, 1058, 5683)
+    assert (d["nphot"], d["next"]) == (177, 113)
+    assert kpp.mech_dims("Hg")["nvar"] == 32 and kpp.mech_dims("carbon")["nvar"] == 12
+    names = kpp.spc_names("fullchem")
+    assert names[0] == "CH2I2" and names[-3:] == ["H2", "N2", "O2"]
+
+
+def test_no_cpu_fallback(lib):
+    """without a CUDA device the product path must fail loudly, not compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        kpp.KppSolver("fullchem")
+    except kpp.KppError as e:
+        assert "gckpp_gpu_init failed" in str(e)
+    else:
+        raise AssertionError("KppSolver constructed without a GPU")
+
+
+def test_product_does_not_touch_oracle():
+    """only tests/, bench.py and __graft_entry__.smoke() may use oracle/"""
+    pkg = os.path.join(ROOT, "geos_chem_b200")
+    for dp, _, fs in os.walk(pkg):
+        if "build" in dp.split(os.sep):
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "kpp_oracle" not in txt and "libkpp_oracle" not in txt, os.path.join(dp, f)
