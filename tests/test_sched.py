@@ -1,0 +1,76 @@
+"""The static round/bundle schedules (geos_chem_b200/kppgen/sched.py) executed by a numpy emulation of
+the kernel's bundle engine must reproduce the oracle's Fun, Jac_SP, KppDecomp+KppSolve
+(KPP/fullchem/gckpp_Function.F90, gckpp_Jacobian.F90, gckpp_LinearAlgebra.F90:46-83, 644-2309)."""
+import numpy as np
+import pytest
+
+from geos_chem_b200 import grid
+from geos_chem_b200.kppgen import ir, sched
+from oracle.pyoracle import Oracle
+
+
+def eval_terms(terms_list, V, F, R):
+    out = np.zeros(len(terms_list))
+    for i, e in enumerate(terms_list):
+        if e is None:
+            continue
+        assert len(e) == 1
+        x = 1.0
+        for k, v in e[0].factors:
+            x *= {"R": lambda: R[v], "V": lambda: V[v], "F": lambda: F[v], "N": lambda: float(v)}[k]()
+        out[i] = x
+    return out
+
+
+@pytest.mark.parametrize("mech", ["fullchem", "Hg"])
+def test_schedule_matches_oracle(mech):
+    m = ir.load(mech)
+    s = sched.Schedule(m)
+    o = Oracle()
+    rng = np.random.default_rng(7)
+    if mech == "fullchem":
+        fx = grid.load_fixture()
+        C = fx["C"] * 10 ** rng.uniform(-0.3, 0.3, m.nspec)
+        R = fx["R"].copy()
+    else:
+        C = 10 ** rng.uniform(3, 9, m.nspec)
+        R = 10 ** rng.uniform(-14, -10, m.nreact)
+    V, F = C[:m.nvar], C[m.nvar:]
+    vdot_o, A_o = o.fun(mech, C, R)
+    A = eval_terms(m.A, V, F, R)
+    np.testing.assert_allclose(A, A_o, rtol=1e-14)
+    vdot = s.emulate_fun(A)
+    scale = np.abs(vdot_o) + 1e-30
+    # aggregate, re-associated sums: compare against the magnitude of the largest contribution
+    big = np.zeros(m.nvar)
+    for i, e in enumerate(m.Vdot):
+        for t in e:
+            c = 1.0
+            idx = None
+            for k, v in t.factors:
+                if k == "N":
+                    c = float(v)
+                else:
+                    idx = v
+            big[i] = max(big[i], abs(c * A[idx]))
+    assert np.all(np.abs(vdot - vdot_o) <= 1e-12 * (big + 1e-300) * 400), np.max(np.abs(vdot - vdot_o) / (big + 1e-300))
+    # Jacobian
+    B = eval_terms(m.B, V, F, R)
+    jvs_o = o.jac(mech, C, R)
+    H, gam = 300.0, 0.5
+    ghinv = 1.0 / (H * gam)
+    G = s.emulate_jac(B, ghinv)
+    Gref = -jvs_o.copy()
+    Gref[np.array(m.lu_diag)] += ghinv
+    np.testing.assert_allclose(G, Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
+    # LU + solve against the oracle's KppDecomp / KppSolve
+    lu_o, ier = o.decomp(mech, Gref)
+    assert ier == 0
+    b = rng.standard_normal(m.nvar) * np.abs(vdot_o).max()
+    x_o = o.solve(mech, lu_o, b)
+    Glu = s.emulate_lu(Gref.copy())
+    x = s.emulate_solve(Glu, b.copy())
+    np.testing.assert_allclose(x, x_o, rtol=1e-9, atol=1e-12 * np.abs(x_o).max())
+    # L multipliers are the reference's; U rows are the reference's divided by the pivot
+    d = np.array(m.lu_diag)
+    np.testing.assert_allclose(Glu[d], 1.0 / lu_o[d], rtol=1e-10)
