@@ -24,6 +24,8 @@ UNITS = {
     "kernels_misc.cu": [],
     # arithmetic-reference kernel: no FMA contraction so sums round like the reference's
     "ros_generic.cu": ["-fmad=false"],
+    # production kernel: shared-memory-resident, FMA allowed
+    "ros_smem.cu": [],
 }
 
 

@@ -14,10 +14,13 @@
 #include "../../include/gckpp_gpu.h"
 #include "ros_common.cuh"
 #include "kernels.h"
+#include "ros_smem.h"
 
 #include "gen/fullchem_tables.h"
 #include "gen/Hg_tables.h"
 #include "gen/carbon_tables.h"
+#include "gen/fullchem_sched.h"
+#include "gen/Hg_sched.h"
 #include "gen/fullchem_names.h"
 #include "gen/Hg_names.h"
 #include "gen/carbon_names.h"
@@ -46,6 +49,15 @@ static const gckpp_host_tables_t *host_tables(int mech_id)
   case GCKPP_MECH_FULLCHEM: return &fullchem_tables;
   case GCKPP_MECH_HG: return &Hg_tables;
   case GCKPP_MECH_CARBON: return &carbon_tables;
+  default: return nullptr;
+  }
+}
+
+static const gckpp_sched_tables_t *host_sched(int mech_id)
+{
+  switch (mech_id) {
+  case GCKPP_MECH_FULLCHEM: return &fullchem_sched;
+  case GCKPP_MECH_HG: return &Hg_sched;
   default: return nullptr;
   }
 }
@@ -82,6 +94,12 @@ struct gckpp_gpu_handle {
   // staging for the host entry points
   DevBuf s_conc_in, s_conc_out, s_rconst, s_met, s_photol, s_khet, s_hstart, s_active, s_ist, s_rst, s_ierr;
   int opt_retry = 0, opt_kernel = -1, opt_sort = 0;
+  // shared-memory kernel: host plan + device copies of its tables
+  int sm_warps = 12, sm_ready = 0, sm_blocks_cap = 0;
+  SmemHostPlan plan;
+  SmemArgs sargs{};
+  DevBuf sm_stream, sm_prog, sm_aw, sm_bw, sm_coefs, sm_diag;
+  int last_kernel = 0;
   double stats[16]{};
 };
 
@@ -188,7 +206,8 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   for (void *p : h->table_allocs) cudaFree(p);
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
-                    &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr};
+                    &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
+                    &h->sm_stream, &h->sm_prog, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -221,6 +240,8 @@ extern "C" int gckpp_gpu_set_option(gckpp_gpu_handle_t *h, const char *key, int 
   else if (!strcmp(key, "kernel")) h->opt_kernel = value;
   else if (!strcmp(key, "sort")) h->opt_sort = value;
   else if (!strcmp(key, "blocks_per_sm")) { if (value < 1 || value > 16) return fail(-10, "blocks_per_sm out of range"); h->blocks_per_sm = value; h->max_blocks = h->sm_count * value; }
+  else if (!strcmp(key, "warps")) { if (value != 8 && value != 12) return fail(-10, "warps must be 8 or 12"); if (value != h->sm_warps) { h->sm_warps = value; h->sm_ready = 0; } }
+  else if (!strcmp(key, "blocks_cap")) { h->sm_blocks_cap = value; }
   else if (!strcmp(key, "threads")) { if (value < 32 || value > 1024 || value % 32) return fail(-10, "threads must be a multiple of 32"); h->threads = value; }
   else return fail(-10, "gckpp_gpu_set_option: unknown option '%s'", key);
   return 0;
@@ -374,14 +395,61 @@ static int ensure_workspace(gckpp_gpu_handle *h, int blocks)
   return 0;
 }
 
+// Upload the tables of the shared-memory kernel once per handle (and per warp-count choice).
+static int prepare_smem(gckpp_gpu_handle *h)
+{
+  if (h->sm_ready) return 0;
+  const gckpp_sched_tables_t *S = host_sched(h->mech_id);
+  if (!S || !smem_kernel_supports(h->T, h->sm_warps)) return fail(-11, "shared-memory kernel not available for this mechanism");
+  if (smem_plan_build(h->T, S, h->sm_warps, h->plan)) return fail(-11, "shared-memory kernel: schedule does not fit the encoding");
+  SmemHostPlan &p = h->plan;
+  int maxsm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if ((size_t)maxsm < p.smem_bytes) return fail(-11, "shared-memory kernel needs %zu bytes of shared memory, device offers %d", p.smem_bytes, maxsm);
+  size_t nprog = p.prog_nb.size();
+  if (h->sm_stream.ensure(p.stream.size() * 4) || h->sm_prog.ensure(nprog * 4) || h->sm_aw.ensure(p.aw.size() * 4) ||
+      h->sm_bw.ensure(p.bw.size() * 4) || h->sm_coefs.ensure(sizeof(double) * (size_t)p.D.ncoef) || h->sm_diag.ensure(p.diag.size() * 2))
+    return fail(-1002, "out of device memory for the kernel tables");
+  CUDA_TRY(cudaMemcpy(h->sm_stream.p, p.stream.data(), p.stream.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->sm_prog.p, p.prog_nb.data(), nprog * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy((char *)h->sm_prog.p + nprog * 2, p.prog_P.data(), nprog * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->sm_aw.p, p.aw.data(), p.aw.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->sm_bw.p, p.bw.data(), p.bw.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->sm_coefs.p, host_sched(h->mech_id)->coefs, sizeof(double) * (size_t)p.D.ncoef, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->sm_diag.p, p.diag.data(), p.diag.size() * 2, cudaMemcpyHostToDevice));
+  SmemArgs &A = h->sargs;
+  A.D = p.D;
+  A.stream = h->sm_stream.as<uint32_t>();
+  for (int w = 0; w < SMEM_MAX_WARPS; w++) { A.warp_off[w] = p.warp_off[w]; A.warp_rows[w] = p.warp_rows[w]; }
+  A.prog_nb = h->sm_prog.as<uint16_t>();
+  A.prog_P = h->sm_prog.as<uint16_t>() + nprog;
+  A.diag = h->sm_diag.as<uint16_t>();
+  A.aw = h->sm_aw.as<uint32_t>(); A.bw = h->sm_bw.as<uint32_t>();
+  A.coefs = h->sm_coefs.as<double>();
+  A.lit = h->M.lit;
+  h->sm_ready = 1;
+  return 0;
+}
+
+// The shared-memory kernel implements the method GEOS-Chem selects (Rodas3, ICNTRL(3) = 0 or 4).
+static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
+{
+  if (h->opt_kernel == 0) return false;
+  if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->T, h->sm_warps)) return false;
+  if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
+  if (d.o.Tstart == d.o.Tend) return false;
+  return true;
+}
+
 static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int nwork, const int *cell_list,
                           const double *conc_in, const double *rconst, const double *hstart,
                           double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
 {
   if (nwork <= 0) return 0;
+  const bool smem = use_smem_kernel(h, d);
   int blocks = (nwork + h->threads - 1) / h->threads;
   if (blocks > h->max_blocks) blocks = h->max_blocks;
-  int rc = ensure_workspace(h, blocks);
+  int rc = smem ? prepare_smem(h) : ensure_workspace(h, blocks);
   if (rc) return rc;
   RosArgs a;
   a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
@@ -394,7 +462,14 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
   if (h->T->nnz == 0) {   // carbon: forward Euler
     CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
+  } else if (smem) {      // one persistent block per SM, SMEM_NC cells each
+    int nb = (nwork + SMEM_NC - 1) / SMEM_NC;
+    if (nb > h->sm_count) nb = h->sm_count;
+    if (h->sm_blocks_cap > 0 && nb > h->sm_blocks_cap) nb = h->sm_blocks_cap;
+    CUDA_TRY(launch_ros_smem(h->sargs, a, h->sm_warps, nb, h->plan.smem_bytes, h->stream));
+    h->last_kernel = 1;
   } else {
+    h->last_kernel = 0;
     CUDA_TRY(launch_ros_generic(h->M, a, blocks, h->threads, h->stream));
   }
   h->stats[6] += 1;

@@ -16,6 +16,14 @@ struct gckpp_host_tables_t {
   const double *lit; int nlit;
 };
 
+// Round/bundle schedules of the shared-memory kernel (kppgen/sched.py documents the encoding).
+struct gckpp_sched_tables_t {
+  int nterms, nlanes, nbundles, nrounds;
+  const uint32_t *terms, *lanes, *bundles /* [nbundles][2] */, *rounds /* [nrounds][3]: first, last+1, kind */;
+  int phase[12];                                       // round ranges of vdot, jvs, lu, scale, fwd, bwd
+  const double *coefs; int ncoef;
+};
+
 // Device copy: same fields, device pointers.
 struct MechDev {
   int nvar, nfix, nspec, nreact, nnz, nb, nphot, next, fun_split;
