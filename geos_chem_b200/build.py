@@ -25,7 +25,7 @@ UNITS = {
     # arithmetic-reference kernel: no FMA contraction so sums round like the reference's
     "ros_generic.cu": ["-fmad=false"],
     # production kernel: shared-memory-resident, FMA allowed
-    "ros_smem.cu": [],
+    "ros_smem.cu": (["-DSMEM_PROFILE"] if os.environ.get("GCKPP_SMEM_PROFILE") else []),
 }
 
 

@@ -190,7 +190,7 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
 #undef UP
   h->L = make_layout(T);
   h->max_blocks = h->sm_count * h->blocks_per_sm;
-  if (h->next.ensure(sizeof(int)) || h->sums.ensure(8 * sizeof(unsigned long long)) ||
+  if (h->next.ensure(sizeof(int)) || h->sums.ensure(16 * sizeof(unsigned long long)) ||
       h->tol.ensure(2 * sizeof(double) * T->nvar) || h->counter.ensure(4 * sizeof(int))) {
     gckpp_gpu_finalize(h);
     return fail(-1002, "gckpp_gpu_init: out of device memory");
@@ -434,7 +434,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
 // The shared-memory kernel implements the method GEOS-Chem selects (Rodas3, ICNTRL(3) = 0 or 4).
 static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
-  if (h->opt_kernel == 0) return false;
+  if (h->opt_kernel != 1) return false;      // default: table-driven kernel until the shared-memory kernel is the faster one
   if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->T, h->sm_warps)) return false;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
   if (d.o.Tstart == d.o.Tend) return false;
@@ -503,7 +503,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 16 * sizeof(unsigned long long), h->stream));
 
   // K1: rate constants
   CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
@@ -533,9 +533,12 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
 
-  unsigned long long sums[8];
+  unsigned long long sums[16];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (getenv("GCKPP_PROFILE"))
+    fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun0 %llu jac %llu lu %llu scale %llu solve %llu fun %llu accept %llu\n",
+            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15]);
   int nfail = (int)sums[2], nfail2 = 0;
   h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
 
@@ -549,7 +552,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     Decoded d2 = d;
     d2.o.Hstart_rcntrl = 0.0;
-    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 16 * sizeof(unsigned long long), h->stream));
     rc = run_integrator(h, d2, ncell, nretry, h->cell_list.as<int>(), conc_in, rconst, nullptr, conc_out, istatus, rstatus, ierr);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));

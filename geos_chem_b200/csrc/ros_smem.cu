@@ -36,6 +36,15 @@
 #include "ros_common.cuh"
 #include "ros_smem.h"
 
+// -DSMEM_PROFILE: thread 0 of block 0 accumulates clock64() per phase into sums[8..]
+#ifdef SMEM_PROFILE
+#define PROF_DECL long long pt_ = clock64(), pacc_[12] = {0,0,0,0,0,0,0,0,0,0,0,0};
+#define PROF(i) do { long long t_ = clock64(); pacc_[i] += t_ - pt_; pt_ = t_; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int RING = 16;             // rows of 32 words per warp in the prefetch ring
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
   rd.L = P.warp_rows[warp]; rd.irow = 0; rd.islot = 0; rd.cslot = 0;
   rd.prime();
   __syncthreads();
+  PROF_DECL
 
   for (;;) {
     // ---- control: TimeLoop tests, retire finished cells, hand out new ones (gckpp_Integrator.F90:652-665)
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
       any |= (slot[c].have != 0);
     }
     if (!any) break;
+    PROF(0);
 
     int rp = 0;       // program round pointer
     // ---- helpers as lambdas ----------------------------------------------------------------------
@@ -375,6 +386,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
 #pragma unroll
       for (int c = 0; c < NC; c++) F0[c] = X[c * N + tid];
     }
+    PROF(1);
     // ---- Ghimj = 1/(H*gamma) - Jac0  (:1973-1977); Jac0 is recomputed per attempt
 #pragma unroll
     for (int k = 0; k < NB_IT; k++) {
@@ -389,6 +401,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     run_round<OP_JVS, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
     rp++;
     __syncthreads();
+    PROF(2);
     // ---- sparse LU  (KppDecomp)
     for (int r = 0; r < D.n_lu; r++, rp++) {
       const int nbk = prog[rp];
@@ -396,6 +409,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
       else run_round<OP_LUUPD, NC, NW>(rd, nbk, warp, D, G, X, SCR, COEF, slot);
       round_barrier<NW>(progP[rp], warp);
     }
+    PROF(3);
     for (int i = tid; i < N; i += NT) {
       const int dp = diag[i];
 #pragma unroll
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     rp++;
     __syncthreads();
 
+    PROF(4);
     // ---- stages (Rodas3: NewF = T,F,T,T; :691-724)
     double dh[NC];
 #pragma unroll
@@ -421,6 +436,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     solve();
+    PROF(5);
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++) {
@@ -431,6 +447,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     solve();
+    PROF(5);
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++) {
@@ -441,6 +458,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     fun_to_X();
+    PROF(6);
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++)
@@ -448,6 +466,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     solve();
+    PROF(5);
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++) {
@@ -458,6 +477,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     fun_to_X();
+    PROF(6);
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++)
@@ -465,6 +485,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     }
     __syncthreads();
     solve();
+    PROF(5);
     // ---- new solution, error estimate and norm  (:729-740, :1715-1745)
     double yn[NC], e2[NC];
 #pragma unroll
@@ -534,7 +555,12 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
         if (slot[c].have && slot[c].accept) Y[c] = o.ClipNegative ? fmax(yn[c], 0.0) : yn[c];
     }
     __syncthreads();      // the control threads rewrite slot[] at the top of the loop
+    PROF(7);
   }
+#ifdef SMEM_PROFILE
+  if (tid == 0 && blockIdx.x == 0 && a.sums)
+    for (int i = 0; i < 8; i++) a.sums[8 + i] = (unsigned long long)pacc_[i];
+#endif
 
   if (tid < NC && a.sums) {
     atomicAdd(a.sums + 0, acc_stp);
