@@ -95,10 +95,10 @@ struct gckpp_gpu_handle {
   DevBuf s_conc_in, s_conc_out, s_rconst, s_met, s_photol, s_khet, s_hstart, s_active, s_ist, s_rst, s_ierr;
   int opt_retry = 0, opt_kernel = -1, opt_sort = 0;
   // shared-memory kernel: host plan + device copies of its tables
-  int sm_warps = 12, sm_ready = 0, sm_blocks_cap = 0;
+  int sm_ready = 0, sm_blocks_cap = 0;
   SmemHostPlan plan;
   SmemArgs sargs{};
-  DevBuf sm_stream, sm_prog, sm_aw, sm_bw, sm_coefs, sm_diag;
+  DevBuf sm_rcs, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
   double stats[16]{};
 };
@@ -190,7 +190,7 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
 #undef UP
   h->L = make_layout(T);
   h->max_blocks = h->sm_count * h->blocks_per_sm;
-  if (h->next.ensure(sizeof(int)) || h->sums.ensure(16 * sizeof(unsigned long long)) ||
+  if (h->next.ensure(sizeof(int)) || h->sums.ensure(32 * sizeof(unsigned long long)) ||
       h->tol.ensure(2 * sizeof(double) * T->nvar) || h->counter.ensure(4 * sizeof(int))) {
     gckpp_gpu_finalize(h);
     return fail(-1002, "gckpp_gpu_init: out of device memory");
@@ -207,7 +207,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
-                    &h->sm_stream, &h->sm_prog, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->sm_rcs, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -240,7 +240,6 @@ extern "C" int gckpp_gpu_set_option(gckpp_gpu_handle_t *h, const char *key, int 
   else if (!strcmp(key, "kernel")) h->opt_kernel = value;
   else if (!strcmp(key, "sort")) h->opt_sort = value;
   else if (!strcmp(key, "blocks_per_sm")) { if (value < 1 || value > 16) return fail(-10, "blocks_per_sm out of range"); h->blocks_per_sm = value; h->max_blocks = h->sm_count * value; }
-  else if (!strcmp(key, "warps")) { if (value != 8 && value != 12) return fail(-10, "warps must be 8 or 12"); if (value != h->sm_warps) { h->sm_warps = value; h->sm_ready = 0; } }
   else if (!strcmp(key, "blocks_cap")) { h->sm_blocks_cap = value; }
   else if (!strcmp(key, "threads")) { if (value < 32 || value > 1024 || value % 32) return fail(-10, "threads must be a multiple of 32"); h->threads = value; }
   else return fail(-10, "gckpp_gpu_set_option: unknown option '%s'", key);
@@ -395,38 +394,46 @@ static int ensure_workspace(gckpp_gpu_handle *h, int blocks)
   return 0;
 }
 
-// Upload the tables of the shared-memory kernel once per handle (and per warp-count choice).
+// Upload the tables of the shared-memory kernel once per handle.
 static int prepare_smem(gckpp_gpu_handle *h)
 {
   if (h->sm_ready) return 0;
   const gckpp_sched_tables_t *S = host_sched(h->mech_id);
-  if (!S || !smem_kernel_supports(h->T, h->sm_warps)) return fail(-11, "shared-memory kernel not available for this mechanism");
-  if (smem_plan_build(h->T, S, h->sm_warps, h->plan)) return fail(-11, "shared-memory kernel: schedule does not fit the encoding");
+  if (!S || !smem_kernel_supports(h->mech_id)) return fail(-11, "shared-memory kernel not available for this mechanism");
+  int prc = smem_plan_build(h->mech_id, h->T, S, h->plan);
+  if (prc) return fail(-11, "shared-memory kernel: plan failed (%d)", prc);
   SmemHostPlan &p = h->plan;
   int maxsm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  if ((size_t)maxsm < p.smem_bytes) return fail(-11, "shared-memory kernel needs %zu bytes of shared memory, device offers %d", p.smem_bytes, maxsm);
-  size_t nprog = p.prog_nb.size();
-  if (h->sm_stream.ensure(p.stream.size() * 4) || h->sm_prog.ensure(nprog * 4) || h->sm_aw.ensure(p.aw.size() * 4) ||
-      h->sm_bw.ensure(p.bw.size() * 4) || h->sm_coefs.ensure(sizeof(double) * (size_t)p.D.ncoef) || h->sm_diag.ensure(p.diag.size() * 2))
-    return fail(-1002, "out of device memory for the kernel tables");
-  CUDA_TRY(cudaMemcpy(h->sm_stream.p, p.stream.data(), p.stream.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->sm_prog.p, p.prog_nb.data(), nprog * 2, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy((char *)h->sm_prog.p + nprog * 2, p.prog_P.data(), nprog * 2, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->sm_aw.p, p.aw.data(), p.aw.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->sm_bw.p, p.bw.data(), p.bw.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->sm_coefs.p, host_sched(h->mech_id)->coefs, sizeof(double) * (size_t)p.D.ncoef, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->sm_diag.p, p.diag.data(), p.diag.size() * 2, cudaMemcpyHostToDevice));
+  if (maxsm < p.s_total + 64) return fail(-11, "shared-memory kernel needs %d bytes of shared memory, device offers %d", p.s_total, maxsm);
+  struct Up { DevBuf *b; const void *src; size_t bytes; };
+  Up ups[] = {
+    {&h->sm_stream, p.stream.data(), p.stream.size() * 4}, {&h->sm_res, p.resident.data(), p.resident.size() * 4},
+    {&h->sm_boff, p.boff.data(), p.boff.size() * 2},       {&h->sm_dir, p.dir.data(), p.dir.size() * 4},
+    {&h->sm_tpos, S->tpos, 32 * 32 * 2},                   {&h->sm_diag, p.diag.data(), p.diag.size() * 2},
+    {&h->sm_crow, p.crow.data(), p.crow.size() * 2},       {&h->sm_aw, p.aw.data(), p.aw.size() * 4},
+    {&h->sm_bw, p.bw.data(), p.bw.size() * 4},             {&h->sm_coefs, S->coefs, sizeof(double) * (size_t)S->ncoef},
+  };
+  for (Up &u : ups) {
+    if (u.b->ensure(u.bytes ? u.bytes : 16)) return fail(-1002, "out of device memory for the kernel tables");
+    if (u.bytes) CUDA_TRY(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+  }
   SmemArgs &A = h->sargs;
-  A.D = p.D;
-  A.stream = h->sm_stream.as<uint32_t>();
-  for (int w = 0; w < SMEM_MAX_WARPS; w++) { A.warp_off[w] = p.warp_off[w]; A.warp_rows[w] = p.warp_rows[w]; }
-  A.prog_nb = h->sm_prog.as<uint16_t>();
-  A.prog_P = h->sm_prog.as<uint16_t>() + nprog;
-  A.diag = h->sm_diag.as<uint16_t>();
+  A.stream = h->sm_stream.as<uint4>();
+  for (int w = 0; w < SMEM_NW; w++) { A.warp_off[w] = p.warp_off[w]; A.warp_rows[w] = p.warp_rows[w]; }
+  A.resident = h->sm_res.as<uint4>(); A.res_rows = (int)(p.resident.size() / 128);
+  A.boff = h->sm_boff.as<uint16_t>(); A.nresb = (int)p.boff.size();
+  A.dir = h->sm_dir.as<uint32_t>(); A.ndir = (int)p.dir.size();
+  A.o_lu = p.o_lu; A.n_lu = p.n_lu; A.o_fwd = p.o_fwd; A.n_fwd = p.n_fwd; A.o_bwd = p.o_bwd; A.n_bwd = p.n_bwd;
+  A.tpos = h->sm_tpos.as<uint16_t>();
+  A.diag = h->sm_diag.as<uint16_t>(); A.crow = h->sm_crow.as<uint16_t>();
   A.aw = h->sm_aw.as<uint32_t>(); A.bw = h->sm_bw.as<uint32_t>();
   A.coefs = h->sm_coefs.as<double>();
   A.lit = h->M.lit;
+  if (h->sm_rcs.ensure(sizeof(double) * smem_rcs_doubles_per_block(h->mech_id) * (size_t)h->sm_count)) return fail(-1002, "out of device memory");
+  A.rcs = h->sm_rcs.as<double>();
+  A.s_res = p.s_res; A.s_tpos = p.s_tpos; A.s_boff = p.s_boff; A.s_dir = p.s_dir; A.s_diag = p.s_diag; A.s_crow = p.s_crow;
+  A.s_total = p.s_total;
   h->sm_ready = 1;
   return 0;
 }
@@ -435,7 +442,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
 static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
   if (h->opt_kernel != 1) return false;      // default: table-driven kernel until the shared-memory kernel is the faster one
-  if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->T, h->sm_warps)) return false;
+  if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->mech_id)) return false;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
   if (d.o.Tstart == d.o.Tend) return false;
   return true;
@@ -466,7 +473,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
     int nb = (nwork + SMEM_NC - 1) / SMEM_NC;
     if (nb > h->sm_count) nb = h->sm_count;
     if (h->sm_blocks_cap > 0 && nb > h->sm_blocks_cap) nb = h->sm_blocks_cap;
-    CUDA_TRY(launch_ros_smem(h->sargs, a, h->sm_warps, nb, h->plan.smem_bytes, h->stream));
+    CUDA_TRY(launch_ros_smem(h->mech_id, h->sargs, a, nb, h->stream));
     h->last_kernel = 1;
   } else {
     h->last_kernel = 0;
@@ -503,7 +510,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 16 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
 
   // K1: rate constants
   CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
@@ -533,12 +540,12 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
 
-  unsigned long long sums[16];
+  unsigned long long sums[32];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (getenv("GCKPP_PROFILE"))
-    fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun0 %llu jac %llu lu %llu scale %llu solve %llu fun %llu accept %llu\n",
-            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15]);
+    fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu\n",
+            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19]);
   int nfail = (int)sums[2], nfail2 = 0;
   h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
 
@@ -552,7 +559,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     Decoded d2 = d;
     d2.o.Hstart_rcntrl = 0.0;
-    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 16 * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
     rc = run_integrator(h, d2, ncell, nretry, h->cell_list.as<int>(), conc_in, rconst, nullptr, conc_out, istatus, rstatus, ierr);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
@@ -752,6 +759,19 @@ extern "C" int gckpp_gpu_solve(gckpp_gpu_handle_t *h, int ncell, const double *j
   CUDA_TRY(launch_solve_cells(h->M, ncell, J, X, h->stream));
   CUDA_TRY(cudaMemcpyAsync(x, X, sizeof(double) * T->nvar * nc, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_plan_info(int mech_id, int32_t *info)
+{
+  const gckpp_host_tables_t *T = host_tables(mech_id);
+  const gckpp_sched_tables_t *S = host_sched(mech_id);
+  if (!T || !S || !info) return fail(-11, "no shared-memory kernel plan for mechanism %d", mech_id);
+  SmemHostPlan p;
+  int rc = smem_plan_build(mech_id, T, S, p);
+  if (rc) return fail(-11, "plan failed (%d)", rc);
+  info[0] = p.s_total; info[1] = (int)(p.stream.size() / 128); info[2] = (int)(p.resident.size() / 128);
+  info[3] = (int)p.dir.size(); info[4] = p.n_lu; info[5] = p.n_fwd; info[6] = p.n_bwd; info[7] = SMEM_NC;
   return 0;
 }
 

@@ -2,12 +2,12 @@
 //
 // Reference routines covered (KPP/fullchem/..., identical structure for KPP/Hg):
 //   ros_Integrator      gckpp_Integrator.F90:578-786      -> ros_smem_kernel (stage loop, error control)
-//   ros_PrepareMatrix   gckpp_Integrator.F90:1921-1999    -> Jacobian rounds + LU rounds + singular test
+//   ros_PrepareMatrix   gckpp_Integrator.F90:1921-1999    -> Jacobian round + LU rounds + tail LU + singular test
 //   ros_ErrorNorm       gckpp_Integrator.F90:1715-1745    -> block reduction per cell
 //   Fun                 gckpp_Function.F90:51-2152        -> rate phase + "vdot" round (aggregate form)
 //   Jac_SP              gckpp_Jacobian.F90:48-20887       -> partials phase + "jvs" round
-//   KppDecomp           gckpp_LinearAlgebra.F90:46-83     -> "lu" rounds (right-looking, DAG levels)
-//   KppSolve            gckpp_LinearAlgebra.F90:644-2309  -> "fwd"/"bwd" rounds (push form)
+//   KppDecomp           gckpp_LinearAlgebra.F90:46-83     -> "lu" rounds (head pivots, DAG levels) + tail_lu
+//   KppSolve            gckpp_LinearAlgebra.F90:644-2309  -> "fwd"/"bwd" rounds (push form) + tail chains
 //
 // Execution model
 //   * One persistent thread block (NW warps) per SM integrates NC cells in LOCK STEP: every block
@@ -16,15 +16,20 @@
 //     per-cell adaptive step counts never idle a slot until the grid is exhausted.
 //   * Everything an attempt touches more than once lives on chip.  Shared memory (per cell): the
 //     sparse matrix G (LU_NONZERO doubles), the state being evaluated Yg, the right-hand side X,
-//     the rate / partial-derivative scratch SCR.  Registers: thread i owns species i of every slot
-//     (Y, Fcn0, K1..K4) and the rate constants of "its" reactions (the rate phase is thread-private).
+//     the rate / partial-derivative scratch SCR; plus the tables of the triangular sweeps, which are
+//     used four times per attempt.  Registers: thread i owns species i of every slot (Y, Fcn0, K1..K3).
 //   * The sparse kernels are table driven (kppgen/sched.py): a round is a set of bundles of 32 lane
-//     items; each table word is applied to all NC cells by the thread that fetched it, which is what
-//     amortises the index traffic.  The tables are laid out per warp in exact consumption order
-//     ("stream"), cyclic over attempts, and prefetched with cp.async into a per-warp shared-memory
-//     ring RING rows ahead -- table latency never sits on the dependency chain of a round.
+//     items; each table word is applied to all NC cells by the thread that fetched it.  The tables
+//     of Fun, Jac and the LU rounds are laid out per warp in exact consumption order ("stream"),
+//     cyclic over attempts, and prefetched with 16-byte cp.async into a per-warp shared-memory ring.
+//   * The last 32 rows/columns (where KPP's ordering concentrates the fill-in) form a sequential
+//     chain in the elimination DAG.  They are handled by ONE WARP PER CELL: the Schur complement is
+//     factorised in registers (lane i = row i, pivot row broadcast by shuffles) and the triangular
+//     sweeps carry x in a register per lane.
 //   * Barriers: a round that keeps P < NW warps busy synchronises only those warps (named barrier P);
-//     runs of single-bundle rounds (the dense tail of the elimination DAG) use __syncwarp only.
+//     single-bundle rounds use __syncwarp only.
+//   * Code size matters (one warp runs long dependent chains; the instruction cache must hold an
+//     attempt): the three function evaluations and four solves of an attempt share one copy of the code.
 //
 // Arithmetic: FP64 throughout, FMA contraction allowed, sums re-associated (see sched.py).  The
 // diagonal of the factors is stored as its reciprocal and U rows are pre-scaled by it, so the four
@@ -32,13 +37,17 @@
 #include <float.h>
 #include <math.h>
 #include <string.h>
+#include <type_traits>
 #include <vector>
 #include "ros_common.cuh"
 #include "ros_smem.h"
+#include "gen/fullchem_dims.h"
+#include "gen/Hg_dims.h"
+#include "../../include/gckpp_gpu.h"
 
 // -DSMEM_PROFILE: thread 0 of block 0 accumulates clock64() per phase into sums[8..]
 #ifdef SMEM_PROFILE
-#define PROF_DECL long long pt_ = clock64(), pacc_[12] = {0,0,0,0,0,0,0,0,0,0,0,0};
+#define PROF_DECL long long pt_ = clock64(), pacc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF(i) do { long long t_ = clock64(); pacc_[i] += t_ - pt_; pt_ = t_; } while (0)
 #else
 #define PROF_DECL
@@ -47,58 +56,90 @@
 
 namespace {
 
-constexpr int RING = 16;             // rows of 32 words per warp in the prefetch ring
-constexpr int KCH = 4;               // table rows consumed per fetch
+constexpr int NC = SMEM_NC, NW = SMEM_NW, RS = SMEM_RS, NT = NW * 32;
+constexpr unsigned TNONE = 0xFFFFu;
 
-enum { OP_VDOT, OP_JVS, OP_LUDIV, OP_LUUPD, OP_SCALE, OP_SOLVE };
+enum { OP_VDOT, OP_JVS, OP_LUDIV, OP_LUUPD, OP_SOLVE };
 
 struct Slot {
-  double T, H, Hexit, Hnew, Texit, ghinv, Err;
+  double T, H, Hexit, Hnew, Texit, ghinv;
   int cell, have, newstep, rejLast, rejMore, nconsec, ierr, skip, sing, accept;
-  int out_cell, in_cell, out_ierr;
+  int out_cell, in_cell, out_ierr, pad_;
   int ist[8], out_ist[8];
   double out_r[3];
 };
 
-// ---- per-warp table stream ------------------------------------------------------------------------
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int align16(int x) { return (x + 15) & ~15; }
+
+// compile-time shared-memory layout of the hot arrays (byte offsets)
+template <class M>
+struct Lay {
+  static constexpr int NYG = M::NSPEC + M::NLIT + 1;       // [VAR, FIX, literals, 1.0]
+  static constexpr int NSCR = cmax(M::NREACT, M::NB);
+  static constexpr int GS = M::NNZ + 1;                    // per-cell stride of G: slot NNZ holds 0.0 (padding terms)
+  static constexpr int oG = 0;
+  static constexpr int oYG = oG + NC * GS * 8;
+  static constexpr int oX = oYG + NC * NYG * 8;
+  static constexpr int oSCR = oX + NC * M::NVAR * 8;
+  static constexpr int oCOEF = oSCR + NC * NSCR * 8;
+  static constexpr int oRED = oCOEF + M::NCOEF * 8;
+  static constexpr int oSLOT = oRED + NW * NC * 8;
+  static constexpr int oRING = align16(oSLOT + NC * (int)sizeof(Slot));
+  static constexpr int oDYN = oRING + NW * RS * 512;        // runtime-sized regions start here
+  static constexpr int NA_IT = (M::NREACT + NT - 1) / NT;
+  static constexpr int NB_IT = (M::NB + NT - 1) / NT;
+};
+
+// ---- per-warp streamed tables: 16 bytes per lane per chunk row, cp.async ring ------------------------
 struct Reader {
-  const uint32_t *gsrc;     // this lane's column of the warp's stream
+  const uint4 *gsrc;        // this lane's column of the warp's stream
   uint32_t ring;            // shared-space byte address of this lane's column of the warp's ring
   int L, irow, islot, cslot;
   __device__ __forceinline__ void issue()
   {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;"
-                 :: "r"(ring + islot * 128), "l"(gsrc + (size_t)irow * 32));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                 :: "r"(ring + islot * 512), "l"(gsrc + (size_t)irow * 32));
     if (++irow == L) irow = 0;
-    if (++islot == RING) islot = 0;
+    if (++islot == RS) islot = 0;
   }
   __device__ __forceinline__ void prime()
   {
-    for (int i = 0; i < RING - 1; i++) issue();
+    for (int i = 0; i < RS - 1; i++) issue();
   }
-  // m (1..KCH, warp uniform) rows
-  __device__ __forceinline__ void fetch(uint32_t (&w)[KCH], int m)
+  __device__ __forceinline__ uint4 next()
   {
-    asm volatile("cp.async.wait_group %0;" :: "n"(RING - 1 - KCH));
-#pragma unroll
-    for (int j = 0; j < KCH; j++)
-      if (j < m) {
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(ring + cslot * 128));
-        if (++cslot == RING) cslot = 0;
-      }
-#pragma unroll
-    for (int j = 0; j < KCH; j++)
-      if (j < m) issue();
-  }
-  __device__ __forceinline__ uint32_t fetch1()
-  {
-    uint32_t w[KCH];
-    fetch(w, 1);
-    return w[0];
+    uint4 v;
+    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 2));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + cslot * 512));
+    if (++cslot == RS) cslot = 0;
+    issue();
+    return v;
   }
 };
 
-template <int NW>
+// resident tables: plain shared-memory reads
+struct ResReader {
+  const uint4 *p;
+  __device__ __forceinline__ uint4 next() { uint4 v = *p; p += 32; return v; }
+};
+
+// a resident bundle whose first two chunks were fetched before the barrier
+struct PreReader {
+  uint4 c0, c1;
+  const uint4 *p;          // third chunk onwards
+  int n;
+  __device__ __forceinline__ uint4 next()
+  {
+    uint4 v;
+    if (n == 0) v = c0;
+    else if (n == 1) v = c1;
+    else { v = *p; p += 32; }
+    n++;
+    return v;
+  }
+};
+
 __device__ __forceinline__ void round_barrier(int P, int warp)
 {
   if (P >= NW) __syncthreads();
@@ -106,110 +147,196 @@ __device__ __forceinline__ void round_barrier(int P, int warp)
   else if (warp < P) asm volatile("bar.sync %0, %1;" :: "r"(P), "r"(P * 32) : "memory");
 }
 
-// One round of the bundle engine for this warp.  nb = bundles of the round (all warps).
-template <int OP, int NC, int NW>
-__device__ __forceinline__ void run_round(Reader &rd, int nb, int warp, const SmemDims &D,
-                                          double *__restrict__ G, double *__restrict__ X,
-                                          const double *__restrict__ SCR, const double *__restrict__ COEF,
-                                          const Slot *slot)
+// One bundle: every lane applies its terms to all NC cells.
+template <class M, int OP, class RD>
+__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot)
 {
-  for (int b = warp; b < nb; b += NW) {
-    const uint32_t lw = rd.fetch1();
-    const int row = lw >> 16, len = (lw >> 8) & 0xff, lg = (lw >> 2) & 7;
-    const int maxlen = __reduce_max_sync(FULLMASK, len);
-    double acc[NC];
+  using L = Lay<M>;
+  double *G = reinterpret_cast<double *>(smem + L::oG);
+  double *X = reinterpret_cast<double *>(smem + L::oX);
+  const uint4 c0 = rd.next();
+  const unsigned lw = c0.x;
+  const int row = lw & 0x1fff, maxlen = (lw >> 19) & 63, lg = (lw >> 25) & 7;
+  double acc[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = 0.0;
-    int first = 0;
-    for (int k0 = 0; k0 < maxlen; k0 += KCH) {
-      uint32_t w[KCH];
-      const int m = min(KCH, maxlen - k0);
-      rd.fetch(w, m);
-      if (k0 == 0) first = w[0] & 0xffff;
-      if (OP == OP_VDOT || OP == OP_JVS || OP == OP_LUUPD || OP == OP_SOLVE) {
+  for (int c = 0; c < NC; c++) acc[c] = 0.0;
+  // Term words carry BYTE offsets; lanes with fewer terms than the bundle are padded with terms whose
+  // product is an exact zero, so every term is loaded and accumulated unconditionally and the loads of
+  // a whole chunk issue back to back.
+  const unsigned char *Gb = smem + L::oG, *Xb = smem + L::oX, *Sb = smem + L::oSCR, *Cb = smem + L::oCOEF;
+  auto ld = [](const unsigned char *base, unsigned off) { return *reinterpret_cast<const double *>(base + off); };
+  auto term = [&](unsigned w) {
+    const unsigned hi = w >> 16, lo = w & 0xffffu;
+    if (OP == OP_VDOT || OP == OP_JVS) {
+      const double cf = ld(Cb, hi);
 #pragma unroll
-        for (int j = 0; j < KCH; j++) {
-          if (j < m && k0 + j < len) {
-            const int hi = w[j] >> 16, lo = w[j] & 0xffff;
-            if (OP == OP_VDOT || OP == OP_JVS) {
-              const double cf = COEF[hi];
+      for (int c = 0; c < NC; c++) acc[c] = fma(cf, ld(Sb + c * L::NSCR * 8, lo), acc[c]);
+    } else if (OP == OP_LUUPD) {
 #pragma unroll
-              for (int c = 0; c < NC; c++) acc[c] = fma(cf, SCR[c * D.nscr + lo], acc[c]);
-            } else if (OP == OP_LUUPD) {
+      for (int c = 0; c < NC; c++) acc[c] = fma(ld(Gb + c * L::GS * 8, hi), ld(Gb + c * L::GS * 8, lo), acc[c]);
+    } else if (OP == OP_SOLVE) {
 #pragma unroll
-              for (int c = 0; c < NC; c++) acc[c] = fma(G[c * D.nnz + hi], G[c * D.nnz + lo], acc[c]);
-            } else {
-#pragma unroll
-              for (int c = 0; c < NC; c++) acc[c] = fma(G[c * D.nnz + hi], X[c * D.nvar + lo], acc[c]);
-            }
-          }
-        }
-      }
+      for (int c = 0; c < NC; c++) acc[c] = fma(ld(Gb + c * L::GS * 8, hi), ld(Xb + c * M::NVAR * 8, lo), acc[c]);
     }
-    if (OP == OP_VDOT || OP == OP_JVS || OP == OP_LUUPD || OP == OP_SOLVE) {
-      for (int s = 0; s < lg; s++) {
+  };
+  if (OP == OP_LUDIV) {
+    if ((lw >> 28) & 1) {
+      const unsigned dp = c0.y & 0xffffu;
 #pragma unroll
-        for (int c = 0; c < NC; c++) acc[c] += __shfl_down_sync(FULLMASK, acc[c], 1 << s);
-      }
+      for (int c = 0; c < NC; c++) G[c * L::GS + row] = G[c * L::GS + row] / ld(Gb + c * L::GS * 8, dp);
     }
-    if (lw & 1) {
-      if (OP == OP_VDOT) {
+    return;
+  }
+  term(c0.y); term(c0.z); term(c0.w);
+  for (int k0 = 3; k0 < maxlen; k0 += 4) {
+    const uint4 cc = rd.next();
+    term(cc.x); term(cc.y); term(cc.z); term(cc.w);
+  }
+  for (int s = 0; s < lg; s++) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) X[c * D.nvar + row] = acc[c];
-      } else if (OP == OP_JVS) {
+    for (int c = 0; c < NC; c++) acc[c] += __shfl_down_sync(FULLMASK, acc[c], 1 << s);
+  }
+  if ((lw >> 28) & 1) {
+    if (OP == OP_VDOT) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) G[c * D.nnz + row] = ((lw & 2) ? slot[c].ghinv : 0.0) - acc[c];
-      } else if (OP == OP_LUUPD) {
+      for (int c = 0; c < NC; c++) X[c * M::NVAR + row] = acc[c];
+    } else if (OP == OP_JVS) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) G[c * D.nnz + row] -= acc[c];
-      } else if (OP == OP_SOLVE) {
+      for (int c = 0; c < NC; c++) G[c * L::GS + row] = (((lw >> 29) & 1) ? slot[c].ghinv : 0.0) - acc[c];
+    } else if (OP == OP_LUUPD) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) X[c * D.nvar + row] -= acc[c];
-      } else if (OP == OP_LUDIV) {
-        if (len) {
+      for (int c = 0; c < NC; c++) G[c * L::GS + row] -= acc[c];
+    } else if (OP == OP_SOLVE) {
 #pragma unroll
-          for (int c = 0; c < NC; c++) G[c * D.nnz + row] = G[c * D.nnz + row] / G[c * D.nnz + first];
-        }
-      } else if (OP == OP_SCALE) {
-        if (len) {
-#pragma unroll
-          for (int c = 0; c < NC; c++) G[c * D.nnz + row] *= G[c * D.nnz + first];
-        }
-      }
+      for (int c = 0; c < NC; c++) X[c * M::NVAR + row] -= acc[c];
     }
   }
 }
 
-template <int NC, int NW, int NA_IT, int NB_IT>
-__global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
+// ---- tail block: one warp per cell ---------------------------------------------------------------------
+// Dense right-looking LU of the Schur complement: lane i holds row i in registers, the pivot row is
+// broadcast with shuffles.  The row registers ROTATE by one column per pivot (r[0] is always the pivot
+// column), so the pivot loop stays rolled and the code small enough for the instruction cache.
+// Entries outside the LU pattern are exact zeros and stay zero (fill-in closure).
+template <class M>
+__device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int lane)
 {
-  constexpr int NT = NW * 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemDims D = P.D;
-  double *G = reinterpret_cast<double *>(smem_raw);          // [NC][nnz]
-  double *Yg = G + NC * D.nnz;                               // [NC][nyg]  state under evaluation + literals + 1.0
-  double *X = Yg + NC * D.nyg;                               // [NC][nvar] right-hand side / solution
-  double *SCR = X + NC * D.nvar;                             // [NC][nscr] A(r) or B(m)
-  double *COEF = SCR + NC * D.nscr;                          // [ncoef]
-  double *RED = COEF + D.ncoef;                              // [NW][NC]
-  Slot *slot = reinterpret_cast<Slot *>(RED + NW * NC);      // [NC]
-  uint32_t *ringbuf = reinterpret_cast<uint32_t *>(slot + NC);   // [NW][RING][32]
-  uint16_t *prog = reinterpret_cast<uint16_t *>(ringbuf + NW * RING * 32);   // [nprog] bundles | P << 8 ... see host
-  uint16_t *progP = prog + D.nprog_pad;                      // [nprog] barrier class after the round
-  uint16_t *diag = progP + D.nprog_pad;                      // [nvar]
+  constexpr int m = M::TAIL;
+  double r[m];
+#pragma unroll
+  for (int k = 0; k < m; k++) {
+    const unsigned p = tposT[k * 32 + lane];
+    r[k] = (p != TNONE) ? Gc[p] : 0.0;
+  }
+#pragma unroll 1
+  for (int j = 0; j < m; j++) {
+    const double dj = __shfl_sync(FULLMASK, r[0], j);
+    const double l = (lane > j) ? r[0] / dj : 0.0;
+    const unsigned p = tposT[j * 32 + lane];
+    if (p != TNONE) Gc[p] = (lane > j) ? l : r[0];         // column j is final: L multiplier, diagonal or U entry
+    // update column j+k and rotate it to slot k-1; shuffles issued in batches so their latency overlaps
+#pragma unroll
+    for (int k0 = 1; k0 < m; k0 += 8) {
+      int hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (k0 + q < m) {
+          hi[q] = __shfl_sync(FULLMASK, __double2hiint(r[k0 + q]), j);
+          lo[q] = __shfl_sync(FULLMASK, __double2loint(r[k0 + q]), j);
+        }
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (k0 + q < m) r[k0 + q - 1] = fma(-l, __hiloint2double(hi[q], lo[q]), r[k0 + q]);
+    }
+    r[m - 1] = 0.0;
+  }
+}
+
+// forward chain on the tail rows: x_i -= L(i,j) x_j, j ascending.  The matrix entries do not depend on
+// the chain, so they are loaded eight columns at a time ahead of the shuffle/FMA chain.
+template <class M>
+__device__ __forceinline__ void tail_fwd(const double *Gc, double *Xc, const uint16_t *tposT, int lane)
+{
+  constexpr int m = M::TAIL;
+  double x = (lane < m) ? Xc[M::HEAD + lane] : 0.0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < m - 1; j0 += 8) {
+    double g[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int j = j0 + q;
+      const unsigned p = (j < m - 1) ? tposT[j * 32 + lane] : TNONE;
+      g[q] = (lane > j && p != TNONE) ? Gc[p] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const double xj = __shfl_sync(FULLMASK, x, (j0 + q) & 31);
+      x = fma(-g[q], xj, x);
+    }
+  }
+  if (lane < m) Xc[M::HEAD + lane] = x;
+}
+
+// backward chain on the tail rows with the scaled U: x_i = b_i/d_i - sum U'(i,j) x_j, j descending
+template <class M>
+__device__ __forceinline__ void tail_bwd(const double *Gc, double *Xc, const uint16_t *tposT, const uint16_t *diag, int lane)
+{
+  constexpr int m = M::TAIL;
+  double x = (lane < m) ? Xc[M::HEAD + lane] * Gc[diag[M::HEAD + (lane < m ? lane : 0)]] : 0.0;
+#pragma unroll 1
+  for (int j0 = m - 1; j0 >= 1; j0 -= 8) {
+    double g[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int j = j0 - q;
+      const unsigned p = (j >= 1) ? tposT[j * 32 + lane] : TNONE;
+      g[q] = (lane < j && p != TNONE) ? Gc[p] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const double xj = __shfl_sync(FULLMASK, x, (j0 - q) & 31);
+      x = fma(-g[q], xj, x);
+    }
+  }
+  if (lane < m) Xc[M::HEAD + lane] = x;
+}
+
+template <class M>
+__global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
+{
+  using L = Lay<M>;
+  static_assert(M::NSPEC <= NT, "one owner thread per species");
+  constexpr int N = M::NVAR, NA_IT = L::NA_IT, NB_IT = L::NB_IT;
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *G = reinterpret_cast<double *>(smem + L::oG);            // [NC][NNZ+1]
+  double *Yg = reinterpret_cast<double *>(smem + L::oYG);          // [NC][NYG] state under evaluation + literals + 1.0
+  double *X = reinterpret_cast<double *>(smem + L::oX);            // [NC][NVAR] right-hand side / solution
+  double *SCR = reinterpret_cast<double *>(smem + L::oSCR);        // [NC][NSCR] A(r) or B(m)
+  double *COEF = reinterpret_cast<double *>(smem + L::oCOEF);
+  double *RED = reinterpret_cast<double *>(smem + L::oRED);        // [NW][NC]
+  Slot *slot = reinterpret_cast<Slot *>(smem + L::oSLOT);          // [NC]
+  uint4 *RES = reinterpret_cast<uint4 *>(smem + P.s_res);          // resident chunk rows
+  uint16_t *tposT = reinterpret_cast<uint16_t *>(smem + P.s_tpos);
+  uint16_t *boff = reinterpret_cast<uint16_t *>(smem + P.s_boff);
+  uint32_t *dir = reinterpret_cast<uint32_t *>(smem + P.s_dir);
+  uint16_t *diag = reinterpret_cast<uint16_t *>(smem + P.s_diag);
+  uint16_t *crow = reinterpret_cast<uint16_t *>(smem + P.s_crow);
   __shared__ int s_exhausted;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const RosOpts &o = a.o;
   const double Dir = (double)o.Direction;
-  const int N = D.nvar;
 
-  for (int i = tid; i < D.ncoef; i += NT) COEF[i] = P.coefs[i];
-  for (int i = tid; i < D.nprog; i += NT) { prog[i] = P.prog_nb[i]; progP[i] = P.prog_P[i]; }
+  for (int i = tid; i < M::NCOEF; i += NT) COEF[i] = P.coefs[i];
+  for (int i = tid; i < P.res_rows * 32; i += NT) RES[i] = P.resident[i];
+  for (int i = tid; i < 32 * 32; i += NT) tposT[i] = P.tpos[i];
+  for (int i = tid; i < P.nresb; i += NT) boff[i] = P.boff[i];
+  for (int i = tid; i < P.ndir; i += NT) dir[i] = P.dir[i];
   for (int i = tid; i < N; i += NT) diag[i] = P.diag[i];
-  for (int i = tid; i < NC * D.nyg; i += NT) {
-    int k = i % D.nyg;
-    Yg[i] = (k < D.nspec) ? 1.0 : (k < D.nspec + D.nlit ? P.lit[k - D.nspec] : 1.0);
+  for (int i = tid; i <= N; i += NT) crow[i] = P.crow[i];
+  for (int i = tid; i < NC * L::NYG; i += NT) {
+    int k = i % L::NYG;
+    Yg[i] = (k < M::NSPEC) ? 1.0 : (k < M::NSPEC + M::NLIT ? P.lit[k - M::NSPEC] : 1.0);
   }
   if (tid < NC) {
     Slot &s = slot[tid];
@@ -218,29 +345,18 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
   }
   if (tid == 0) s_exhausted = 0;
 
-  // thread-private tables: the reactions (rate phase) and partial derivatives (Jacobian phase) of this thread
-  uint32_t aw0[NA_IT], aw1[NA_IT], bw0[NB_IT], bw1[NB_IT];
-  double rcA[NA_IT][NC], rcB[NB_IT][NC];
-#pragma unroll
-  for (int k = 0; k < NA_IT; k++) {
-    int r = k * NT + tid;
-    aw0[k] = r < D.nreact ? P.aw[2 * r] : 0xffffffffu;
-    aw1[k] = r < D.nreact ? P.aw[2 * r + 1] : 0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) rcA[k][c] = 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < NB_IT; k++) {
-    int m = k * NT + tid;
-    bw0[k] = m < D.nb ? P.bw[2 * m] : 0xffffffffu;
-    bw1[k] = m < D.nb ? P.bw[2 * m + 1] : 0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) rcB[k][c] = 0.0;
-  }
+  // The rate phases are thread-private: thread t evaluates reactions t, t+NT, ... (and the partial
+  // derivatives t, t+NT, ... of the Jacobian).  Their rate constants are kept in ITEM order in a
+  // per-block global scratch (written by the same thread when a cell is loaded, L2 resident), and
+  // the encoded terms are re-read from the table: one coalesced load latency per phase instead of
+  // ~50 registers per thread.
+  double *rcsA = P.rcs + (size_t)blockIdx.x * NC * (NA_IT + NB_IT) * NT;     // [NC][NA_IT][NT]
+  double *rcsB = rcsA + (size_t)NC * NA_IT * NT;                               // [NC][NB_IT][NT]
+  const uint2 *awt = reinterpret_cast<const uint2 *>(P.aw), *bwt = reinterpret_cast<const uint2 *>(P.bw);
   // owner registers: thread i holds species i of every slot
-  double Y[NC], F0[NC], K1[NC], K2[NC], K3[NC], K4[NC];
+  double Y[NC], F0[NC], K1[NC], K2[NC], K3[NC];
 #pragma unroll
-  for (int c = 0; c < NC; c++) { Y[c] = 1.0; F0[c] = K1[c] = K2[c] = K3[c] = K4[c] = 0.0; }
+  for (int c = 0; c < NC; c++) { Y[c] = 1.0; F0[c] = K1[c] = K2[c] = K3[c] = 0.0; }
   double atol_i = 1.0, rtol_i = 1.0;
   if (tid < N) {
     atol_i = o.VectorTol ? a.atol[tid] : a.atol[0];
@@ -250,11 +366,18 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
 
   Reader rd;
   rd.gsrc = P.stream + (size_t)P.warp_off[warp] * 32 + lane;
-  rd.ring = (uint32_t)__cvta_generic_to_shared(ringbuf + (warp * RING) * 32 + lane);
+  rd.ring = (uint32_t)__cvta_generic_to_shared(smem + L::oRING + warp * RS * 512 + lane * 16);
   rd.L = P.warp_rows[warp]; rd.irow = 0; rd.islot = 0; rd.cslot = 0;
   rd.prime();
   __syncthreads();
   PROF_DECL
+
+  // a streamed round: this warp's bundles arrive in order through its ring
+  auto stream_round = [&](auto opc, unsigned d) {
+    const int nb = d & 0xfff, W = (d >> 12) & 15;
+    if (warp < W)
+      for (int b = warp; b < nb; b += W) run_bundle<M, decltype(opc)::value>(rd, smem, slot);
+  };
 
   for (;;) {
     // ---- control: TimeLoop tests, retire finished cells, hand out new ones (gckpp_Integrator.F90:652-665)
@@ -312,190 +435,230 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     for (int c = 0; c < NC; c++) {
       const int oc = slot[c].out_cell, ic = slot[c].in_cell;
       if (oc >= 0) {
-        if (tid < D.nspec) a.conc_out[(size_t)tid * a.ncell + oc] = Y[c];
+        if (tid < M::NSPEC) a.conc_out[(size_t)tid * a.ncell + oc] = Y[c];
         if (tid < 8 && a.istatus) a.istatus[(size_t)tid * a.ncell + oc] = slot[c].out_ist[tid];
         if (tid >= 32 && tid < 35 && a.rstatus) a.rstatus[(size_t)(tid - 32) * a.ncell + oc] = slot[c].out_r[tid - 32];
         if (tid == 35 && a.rstatus) a.rstatus[(size_t)3 * a.ncell + oc] = 0.0;
         if (tid == 36 && a.ierr) a.ierr[oc] = slot[c].out_ierr;
       }
       if (ic >= 0) {
-        if (tid < D.nspec) Y[c] = a.conc_in[(size_t)tid * a.ncell + ic];
+        if (tid < M::NSPEC) Y[c] = a.conc_in[(size_t)tid * a.ncell + ic];
 #pragma unroll
         for (int k = 0; k < NA_IT; k++) {
-          int i0 = aw0[k] & 0xffff;
-          if (aw0[k] != 0xffffffffu) rcA[k][c] = i0 < D.nreact ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - D.nreact];
+          const int r = k * NT + tid;
+          if (r < M::NREACT) {
+            const int i0 = awt[r].x & 0xffff;
+            rcsA[(c * NA_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - M::NREACT];
+          }
         }
 #pragma unroll
         for (int k = 0; k < NB_IT; k++) {
-          int i0 = bw0[k] & 0xffff;
-          if (bw0[k] != 0xffffffffu) rcB[k][c] = i0 < D.nreact ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - D.nreact];
+          const int m = k * NT + tid;
+          if (m < M::NB) {
+            const int i0 = bwt[m].x & 0xffff;
+            rcsB[(c * NB_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - M::NREACT];
+          }
         }
       } else if (!slot[c].have) {
-        if (tid < D.nspec) Y[c] = 1.0;      // idle slot: benign numbers
+        if (tid < M::NSPEC) Y[c] = 1.0;      // idle slot: benign numbers
       }
       any |= (slot[c].have != 0);
     }
     if (!any) break;
     PROF(0);
-
-    int rp = 0;       // program round pointer
-    // ---- helpers as lambdas ----------------------------------------------------------------------
-    auto rate_phase = [&]() {       // A(r) = RCT(r) * prod(V)  (Fun, first half)
-#pragma unroll
-      for (int k = 0; k < NA_IT; k++) {
-        if (aw0[k] != 0xffffffffu) {
-          const int r = k * NT + tid, i1 = aw0[k] >> 16, i2 = aw1[k] & 0xffff, i3 = aw1[k] >> 16;
-#pragma unroll
-          for (int c = 0; c < NC; c++)
-            SCR[c * D.nscr + r] = rcA[k][c] * Yg[c * D.nyg + i1] * Yg[c * D.nyg + i2] * Yg[c * D.nyg + i3];
-        }
-      }
-    };
-    auto solve = [&]() {            // KppSolve on X in place
-      for (int r = 0; r < D.n_fwd; r++, rp++) {
-        run_round<OP_SOLVE, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
-        round_barrier<NW>(progP[rp], warp);
-      }
-      for (int i = tid; i < N; i += NT) {
-        const int dp = diag[i];
-#pragma unroll
-        for (int c = 0; c < NC; c++) X[c * N + i] *= G[c * D.nnz + dp];
-      }
-      __syncthreads();
-      for (int r = 0; r < D.n_bwd; r++, rp++) {
-        run_round<OP_SOLVE, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
-        round_barrier<NW>(progP[rp], warp);
-      }
-    };
-    auto fun_to_X = [&]() {         // X = Fun(Yg)
-      rate_phase();
-      __syncthreads();
-      run_round<OP_VDOT, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
-      rp++;
-      __syncthreads();
-    };
-
-    // ---- Fcn0 = Fun(Y)  (:668)
-    if (tid < D.nspec) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) Yg[c * D.nyg + tid] = Y[c];
-    }
-    __syncthreads();
-    fun_to_X();
-    if (tid < N) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) F0[c] = X[c * N + tid];
-    }
-    PROF(1);
-    // ---- Ghimj = 1/(H*gamma) - Jac0  (:1973-1977); Jac0 is recomputed per attempt
-#pragma unroll
-    for (int k = 0; k < NB_IT; k++) {
-      if (bw0[k] != 0xffffffffu) {
-        const int m = k * NT + tid, i1 = bw0[k] >> 16, i2 = bw1[k] & 0xffff, i3 = bw1[k] >> 16;
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-          SCR[c * D.nscr + m] = rcB[k][c] * Yg[c * D.nyg + i1] * Yg[c * D.nyg + i2] * Yg[c * D.nyg + i3];
-      }
-    }
-    __syncthreads();
-    run_round<OP_JVS, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
-    rp++;
-    __syncthreads();
-    PROF(2);
-    // ---- sparse LU  (KppDecomp)
-    for (int r = 0; r < D.n_lu; r++, rp++) {
-      const int nbk = prog[rp];
-      if (nbk & 0x8000) run_round<OP_LUDIV, NC, NW>(rd, nbk & 0x7fff, warp, D, G, X, SCR, COEF, slot);
-      else run_round<OP_LUUPD, NC, NW>(rd, nbk, warp, D, G, X, SCR, COEF, slot);
-      round_barrier<NW>(progP[rp], warp);
-    }
-    PROF(3);
-    for (int i = tid; i < N; i += NT) {
-      const int dp = diag[i];
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        const double d = G[c * D.nnz + dp];
-        if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;          // also catches NaN from an earlier zero pivot
-        G[c * D.nnz + dp] = 1.0 / d;
-      }
-    }
-    __syncthreads();
-    run_round<OP_SCALE, NC, NW>(rd, prog[rp], warp, D, G, X, SCR, COEF, slot);
-    rp++;
-    __syncthreads();
-
-    PROF(4);
-    // ---- stages (Rodas3: NewF = T,F,T,T; :691-724)
     double dh[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) dh[c] = Dir * slot[c].H;
-    // stage 1: K1 = Fcn0
-    if (tid < N) {
+    // Three function evaluations per attempt (Rodas3: NewF = T,F,T,T; :691-724): Fcn0 (followed by the
+    // Jacobian, the LU and stages 1-2), stage 3, stage 4.  One copy of the Fun and solve code.
+#pragma unroll 1
+    for (int ip = 0; ip < 3; ip++) {
+      // ---- the state to evaluate
+      if (ip == 0) {
+        if (tid < M::NSPEC) {
 #pragma unroll
-      for (int c = 0; c < NC; c++) X[c * N + tid] = F0[c];
-    }
-    __syncthreads();
-    solve();
-    PROF(5);
-    if (tid < N) {
+          for (int c = 0; c < NC; c++) Yg[c * L::NYG + tid] = Y[c];
+        }
+      } else if (tid < N) {
 #pragma unroll
-      for (int c = 0; c < NC; c++) {
-        K1[c] = X[c * N + tid];
-        // stage 2: K2 = Fcn0 + C21/H K1
-        X[c * N + tid] = fma(o.C[0] / dh[c], K1[c], F0[c]);
+        for (int c = 0; c < NC; c++)
+          Yg[c * L::NYG + tid] = (ip == 1) ? fma(o.A[2], K2[c], fma(o.A[1], K1[c], Y[c]))
+                                           : fma(o.A[5], K3[c], fma(o.A[4], K2[c], fma(o.A[3], K1[c], Y[c])));
+      }
+      __syncthreads();
+      // ---- X = Fun(Yg): A(r) = RCT(r) * prod(V) by the thread that owns reaction r, then the vdot round
+      {
+        uint2 w[NA_IT];
+        double rc[NA_IT][NC];
+#pragma unroll
+        for (int k = 0; k < NA_IT; k++) {
+          const int r = k * NT + tid;
+          w[k] = r < M::NREACT ? awt[r] : make_uint2(0, 0);
+#pragma unroll
+          for (int c = 0; c < NC; c++) rc[k][c] = r < M::NREACT ? rcsA[(c * NA_IT + k) * NT + tid] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NA_IT; k++) {
+          const int r = k * NT + tid;
+          if (r < M::NREACT) {
+            const int i1 = w[k].x >> 16, i2 = w[k].y & 0xffff, i3 = w[k].y >> 16;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+              SCR[c * L::NSCR + r] = rc[k][c] * Yg[c * L::NYG + i1] * Yg[c * L::NYG + i2] * Yg[c * L::NYG + i3];
+          }
+        }
+      }
+      __syncthreads();
+      stream_round(std::integral_constant<int, OP_VDOT>(), dir[0]);
+      __syncthreads();
+      PROF(1);
+      if (ip == 0) {
+        if (tid < N) {
+#pragma unroll
+          for (int c = 0; c < NC; c++) F0[c] = X[c * N + tid];
+        }
+        // ---- Ghimj = 1/(H*gamma) - Jac0  (:1973-1977); Jac0 is recomputed per attempt
+        {
+          uint2 w[NB_IT];
+          double rc[NB_IT][NC];
+#pragma unroll
+          for (int k = 0; k < NB_IT; k++) {
+            const int m = k * NT + tid;
+            w[k] = m < M::NB ? bwt[m] : make_uint2(0, 0);
+#pragma unroll
+            for (int c = 0; c < NC; c++) rc[k][c] = m < M::NB ? rcsB[(c * NB_IT + k) * NT + tid] : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < NB_IT; k++) {
+            const int m = k * NT + tid;
+            if (m < M::NB) {
+              const int i1 = w[k].x >> 16, i2 = w[k].y & 0xffff, i3 = w[k].y >> 16;
+#pragma unroll
+              for (int c = 0; c < NC; c++)
+                SCR[c * L::NSCR + m] = rc[k][c] * Yg[c * L::NYG + i1] * Yg[c * L::NYG + i2] * Yg[c * L::NYG + i3];
+            }
+          }
+        }
+        for (int i = tid; i < NC * L::GS; i += NT) G[i] = 0.0;        // structural zeros / fill-in slots / zero slot
+        __syncthreads();
+        stream_round(std::integral_constant<int, OP_JVS>(), dir[1]);
+        __syncthreads();
+        PROF(2);
+        // ---- sparse LU  (KppDecomp): head pivots by DAG level, then the tail block
+#pragma unroll 1
+        for (int r = 0; r < P.n_lu; r++) {
+          const unsigned d = dir[P.o_lu + r];
+          if ((d >> 20) & 1) stream_round(std::integral_constant<int, OP_LUDIV>(), d);
+          else stream_round(std::integral_constant<int, OP_LUUPD>(), d);
+          round_barrier((d >> 16) & 15, warp);
+        }
+        PROF(3);
+        if (warp < NC) tail_lu<M>(G + warp * L::GS, tposT, lane);
+        __syncthreads();
+        PROF(4);
+        // row i: singular test (:1985), reciprocal diagonal, U row scaled by it
+        if (tid < N) {
+          const int dp = diag[tid], e = crow[tid + 1];
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const double d = G[c * L::GS + dp];
+            if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;          // also catches NaN from an earlier zero pivot
+            const double rdv = 1.0 / d;
+            G[c * L::GS + dp] = rdv;
+            for (int p = dp + 1; p < e; p++) G[c * L::GS + p] *= rdv;
+          }
+        }
+        PROF(5);
+      }
+      // ---- the stages that use this evaluation: ip 0 -> stages 1 and 2, ip 1 -> stage 3, ip 2 -> stage 4
+      const int nsolve = (ip == 0) ? 2 : 1;
+#pragma unroll 1
+      for (int q = 0; q < nsolve; q++) {
+        const int st = (ip == 0) ? q : ip + 1;
+        if (tid < N) {          // right-hand side K_st = Fcn + sum_j C(st,j)/H K_j
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            double v;
+            if (st == 0) v = F0[c];
+            else if (st == 1) v = fma(o.C[0] / dh[c], K1[c], F0[c]);
+            else if (st == 2) v = fma(o.C[2] / dh[c], K2[c], fma(o.C[1] / dh[c], K1[c], X[c * N + tid]));
+            else v = fma(o.C[5] / dh[c], K3[c], fma(o.C[4] / dh[c], K2[c], fma(o.C[3] / dh[c], K1[c], X[c * N + tid])));
+            X[c * N + tid] = v;
+          }
+        }
+        __syncthreads();
+        // ---- KppSolve on X in place: head of L (rounds), tail chains, head of U (rounds).
+        // The tables do not depend on the data, so the directory entry and the first two chunks of
+        // the NEXT round are fetched before waiting on the barrier of the current one.
+        const int n_tot = P.n_fwd + P.n_bwd;
+        auto prefetch = [&](int r, unsigned &d, PreReader &pr) {
+          d = 0; pr.n = 0; pr.p = RES + lane;
+          if (r < n_tot) {
+            d = dir[P.o_fwd + r];
+            if (warp < (int)((d >> 12) & 15)) {
+              const uint4 *p = RES + (size_t)boff[(d >> 21) + warp] * 32 + lane;
+              pr.c0 = p[0]; pr.c1 = p[32]; pr.p = p + 64;
+            }
+          }
+        };
+        unsigned dn; PreReader pn;
+        PROF(6);
+        prefetch(0, dn, pn);
+#pragma unroll 1
+        for (int r = 0;; r++) {
+          if (r == P.n_fwd) {
+            if (warp < NC) tail_fwd<M>(G + warp * L::GS, X + warp * N, tposT, lane);
+            __syncthreads();
+            if (warp < NC) {
+              tail_bwd<M>(G + warp * L::GS, X + warp * N, tposT, diag, lane);
+            } else {
+              for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
+                const int dp = diag[i];
+#pragma unroll
+                for (int c = 0; c < NC; c++) X[c * N + i] *= G[c * L::GS + dp];
+              }
+            }
+            __syncthreads();
+            PROF(11);
+          }
+          if (r == n_tot) break;
+          const unsigned d = dn;
+          const int nb = d & 0xfff, W = (d >> 12) & 15, bf = d >> 21;
+          if (warp < W) {
+            run_bundle<M, OP_SOLVE>(pn, smem, slot);
+            for (int b = warp + W; b < nb; b += W) {       // only if a round has more bundles than warps
+              ResReader rr;
+              rr.p = RES + (size_t)boff[bf + b] * 32 + lane;
+              run_bundle<M, OP_SOLVE>(rr, smem, slot);
+            }
+          }
+          PROF(8);
+          prefetch(r + 1, dn, pn);
+          PROF(9);
+          round_barrier((d >> 16) & 15, warp);
+          PROF(10);
+        }
+        if (tid < N) {
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const double v = X[c * N + tid];
+            if (st == 0) K1[c] = v;
+            else if (st == 1) K2[c] = v;
+            else if (st == 2) K3[c] = v;
+          }
+        }
       }
     }
-    __syncthreads();
-    solve();
-    PROF(5);
-    if (tid < N) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        K2[c] = X[c * N + tid];
-        // stage 3: Ynew = Y + A31 K1 + A32 K2
-        Yg[c * D.nyg + tid] = fma(o.A[2], K2[c], fma(o.A[1], K1[c], Y[c]));
-      }
-    }
-    __syncthreads();
-    fun_to_X();
-    PROF(6);
-    if (tid < N) {
-#pragma unroll
-      for (int c = 0; c < NC; c++)
-        X[c * N + tid] = fma(o.C[2] / dh[c], K2[c], fma(o.C[1] / dh[c], K1[c], X[c * N + tid]));
-    }
-    __syncthreads();
-    solve();
-    PROF(5);
-    if (tid < N) {
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        K3[c] = X[c * N + tid];
-        // stage 4: Ynew = Y + A41 K1 + A42 K2 + A43 K3
-        Yg[c * D.nyg + tid] = fma(o.A[5], K3[c], fma(o.A[4], K2[c], fma(o.A[3], K1[c], Y[c])));
-      }
-    }
-    __syncthreads();
-    fun_to_X();
-    PROF(6);
-    if (tid < N) {
-#pragma unroll
-      for (int c = 0; c < NC; c++)
-        X[c * N + tid] = fma(o.C[5] / dh[c], K3[c], fma(o.C[4] / dh[c], K2[c], fma(o.C[3] / dh[c], K1[c], X[c * N + tid])));
-    }
-    __syncthreads();
-    solve();
-    PROF(5);
-    // ---- new solution, error estimate and norm  (:729-740, :1715-1745)
+    // ---- new solution, error estimate and norm  (:729-740, :1715-1745); K4 is read from X
     double yn[NC], e2[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) { yn[c] = 0.0; e2[c] = 0.0; }
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++) {
-        K4[c] = X[c * N + tid];
-        yn[c] = fma(o.M[3], K4[c], fma(o.M[2], K3[c], fma(o.M[1], K2[c], fma(o.M[0], K1[c], Y[c]))));
-        const double ye = fma(o.E[3], K4[c], fma(o.E[2], K3[c], fma(o.E[1], K2[c], o.E[0] * K1[c])));
+        const double k4 = X[c * N + tid];
+        yn[c] = fma(o.M[3], k4, fma(o.M[2], K3[c], fma(o.M[1], K2[c], fma(o.M[0], K1[c], Y[c]))));
+        const double ye = fma(o.E[3], k4, fma(o.E[2], K3[c], fma(o.E[1], K2[c], o.E[0] * K1[c])));
         const double sc = atol_i + rtol_i * fmax(fabs(Y[c]), fabs(yn[c]));
         const double q = ye / sc;
         e2[c] = q * q;
@@ -552,16 +715,15 @@ __global__ void __launch_bounds__(NW * 32, 1) ros_smem_kernel(SmemArgs P, RosArg
     if (tid < N) {
 #pragma unroll
       for (int c = 0; c < NC; c++)
-        if (slot[c].have && slot[c].accept) Y[c] = o.ClipNegative ? fmax(yn[c], 0.0) : yn[c];
+        if (slot[c].accept) Y[c] = o.ClipNegative ? fmax(yn[c], 0.0) : yn[c];
     }
     __syncthreads();      // the control threads rewrite slot[] at the top of the loop
     PROF(7);
   }
 #ifdef SMEM_PROFILE
   if (tid == 0 && blockIdx.x == 0 && a.sums)
-    for (int i = 0; i < 8; i++) a.sums[8 + i] = (unsigned long long)pacc_[i];
+    for (int i = 0; i < 16; i++) a.sums[8 + i] = (unsigned long long)pacc_[i];
 #endif
-
   if (tid < NC && a.sums) {
     atomicAdd(a.sums + 0, acc_stp);
     atomicAdd(a.sums + 1, acc_acc);
@@ -589,122 +751,123 @@ static void encode_term(const int *t, int nreact, int nspec, int nlit, uint32_t 
   out[1] = fac(t[2]) | (fac(t[3]) << 16);
 }
 
-int smem_plan_build(const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, int NW, SmemHostPlan &hp)
+template <class M> static int dyn_offset() { return Lay<M>::oDYN; }
+template <class M> static bool dims_match(const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S)
 {
-  const int NC = SMEM_NC;
-  SmemDims &D = hp.D;
-  D.nvar = T->nvar; D.nspec = T->nspec; D.nreact = T->nreact; D.nnz = T->nnz; D.nb = T->nb;
-  D.nlit = T->nlit; D.nyg = T->nspec + T->nlit + 1; D.nscr = T->nreact > T->nb ? T->nreact : T->nb;
-  D.ncoef = S->ncoef;
+  return T->nvar == M::NVAR && T->nspec == M::NSPEC && T->nreact == M::NREACT && T->nnz == M::NNZ && T->nb == M::NB &&
+         T->nlit == M::NLIT && S->ncoef == M::NCOEF && S->tail == M::TAIL && S->head == M::HEAD;
+}
+
+template <class M> static size_t rcs_doubles() { return (size_t)NC * (Lay<M>::NA_IT + Lay<M>::NB_IT) * NT; }
+size_t smem_rcs_doubles_per_block(int mech_id)
+{
+  return mech_id == GCKPP_MECH_FULLCHEM ? rcs_doubles<fullchem_dims>() : rcs_doubles<Hg_dims>();
+}
+
+bool smem_kernel_supports(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM || mech_id == GCKPP_MECH_HG; }
+
+int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, SmemHostPlan &hp)
+{
+  if (!smem_kernel_supports(mech_id)) return -1;
+  if (mech_id == GCKPP_MECH_FULLCHEM ? !dims_match<fullchem_dims>(T, S) : !dims_match<Hg_dims>(T, S)) return -2;
   const int *ph = S->phase;
-  auto nrounds = [&](int p) { return ph[2 * p + 1] - ph[2 * p]; };
-  D.n_lu = nrounds(2); D.n_fwd = nrounds(4); D.n_bwd = nrounds(5);
-  if (nrounds(0) != 1 || nrounds(1) != 1 || nrounds(3) != 1) return -1;
-  // program = sequence of schedule rounds of one Rodas3 attempt
-  std::vector<int> prg;
-  auto push_phase = [&](int p) { for (int r = ph[2 * p]; r < ph[2 * p + 1]; r++) prg.push_back(r); };
-  auto push_solve = [&]() { push_phase(4); push_phase(5); };
-  std::vector<int> phase_end;   // program indices after which every warp must synchronise
-  auto mark_end = [&]() { phase_end.push_back((int)prg.size() - 1); };
-  push_phase(0); mark_end();               // Fcn0
-  push_phase(1); mark_end();               // Jacobian
-  push_phase(2); mark_end();               // LU
-  push_phase(3); mark_end();               // scale
-  for (int st = 0; st < 4; st++) {
-    if (st >= 2) { push_phase(0); mark_end(); }
-    push_phase(4); mark_end();
-    push_phase(5); mark_end();
+  auto r0 = [&](int p) { return ph[2 * p]; };
+  auto r1 = [&](int p) { return ph[2 * p + 1]; };
+  if (r1(0) - r0(0) != 1 || r1(1) - r0(1) != 1) return -3;
+  auto nbundles = [&](int r) { return (int)(S->rounds[3 * r + 1] - S->rounds[3 * r]); };
+  auto nwarps = [&](int r) { int nb = nbundles(r); return nb < NW ? nb : NW; };
+  // directory: vdot, jvs, lu..., fwd..., bwd...
+  std::vector<int> dr;
+  dr.push_back(r0(0)); dr.push_back(r0(1));
+  hp.o_lu = (int)dr.size(); hp.n_lu = r1(2) - r0(2);
+  for (int r = r0(2); r < r1(2); r++) dr.push_back(r);
+  hp.o_fwd = (int)dr.size(); hp.n_fwd = r1(4) - r0(4);
+  for (int r = r0(4); r < r1(4); r++) dr.push_back(r);
+  hp.o_bwd = (int)dr.size(); hp.n_bwd = r1(5) - r0(5);
+  for (int r = r0(5); r < r1(5); r++) dr.push_back(r);
+  // resident bundles: all bundles of the fwd and bwd rounds, in directory order
+  hp.resident.clear(); hp.boff.clear();
+  std::vector<int> bfirst(dr.size(), 0);
+  for (size_t i = (size_t)hp.o_fwd; i < dr.size(); i++) {
+    int r = dr[i];
+    bfirst[i] = (int)hp.boff.size();
+    for (uint32_t b = S->rounds[3 * r]; b < S->rounds[3 * r + 1]; b++) {
+      hp.boff.push_back((uint16_t)(hp.resident.size() / 128));
+      for (uint32_t row = S->brow[b]; row < S->brow[b + 1]; row++)
+        hp.resident.insert(hp.resident.end(), S->chunks + (size_t)row * 128, S->chunks + (size_t)(row + 1) * 128);
+    }
   }
-  (void)push_solve;
-  const int np = (int)prg.size();
-  D.nprog = np; D.nprog_pad = (np + 7) & ~7;
-  hp.prog_nb.assign(np, 0); hp.prog_P.assign(np, 0);
-  std::vector<char> is_end(np, 0);
-  for (int e : phase_end) is_end[e] = 1;
-  for (int i = 0; i < np; i++) {
-    const uint32_t *rr = S->rounds + 3 * prg[i];
-    int nb = (int)(rr[1] - rr[0]);
-    if (nb >= 0x8000) return -1;
-    hp.prog_nb[i] = (uint16_t)(nb | ((rr[2] & 0x10) ? 0x8000 : 0));
+  hp.resident.insert(hp.resident.end(), 128, 0u);      // the kernel prefetches one chunk row past a bundle
+  if (hp.boff.size() >= 2048 || hp.resident.size() / 128 >= 65536) return -4;
+  hp.dir.assign(dr.size(), 0);
+  for (size_t i = 0; i < dr.size(); i++) {
+    int r = dr[i], nb = nbundles(r), W = nwarps(r);
+    if (nb >= 4096) return -4;
+    bool last = (i + 1 == dr.size()) || (int)i + 1 == hp.o_lu || (int)i + 1 == hp.o_fwd || (int)i + 1 == hp.o_bwd || i < 2;
+    int Wn = last ? NW : nwarps(dr[i + 1]);
+    int Pb = last ? NW : (W > Wn ? W : Wn);
+    uint32_t div = (S->rounds[3 * r + 2] & 0x10) ? 1u : 0u;
+    hp.dir[i] = (uint32_t)nb | ((uint32_t)W << 12) | ((uint32_t)Pb << 16) | (div << 20) | ((uint32_t)bfirst[i] << 21);
   }
-  for (int i = 0; i < np; i++) {
-    int nb = hp.prog_nb[i] & 0x7fff;
-    int nn = (i + 1 < np) ? (hp.prog_nb[i + 1] & 0x7fff) : NW;
-    int Pb = nb > nn ? nb : nn;
-    if (Pb > NW || is_end[i]) Pb = NW;
-    hp.prog_P[i] = (uint16_t)Pb;
-  }
-  // per-warp streams in consumption order
+  // per-warp streams: vdot, jvs, lu rounds, vdot, vdot (one Rodas3 attempt)
+  std::vector<int> order;
+  order.push_back(r0(0)); order.push_back(r0(1));
+  for (int r = r0(2); r < r1(2); r++) order.push_back(r);
+  order.push_back(r0(0)); order.push_back(r0(0));
   std::vector<std::vector<uint32_t>> ws(NW);
-  for (int i = 0; i < np; i++) {
-    const uint32_t *rr = S->rounds + 3 * prg[i];
-    for (uint32_t b = rr[0]; b < rr[1]; b++) {
-      int w = (int)((b - rr[0]) % NW);
-      uint32_t base = S->bundles[2 * b], ml = S->bundles[2 * b + 1];
-      uint32_t maxlen = ml & 0xff, lg = ml >> 8;
-      for (int l = 0; l < 32; l++) {
-        uint32_t lw = S->lanes[b * 32 + l];
-        ws[w].push_back((lw & 0xffffff03u) | (lg << 2));
-      }
-      for (uint32_t k = 0; k < maxlen; k++)
-        for (int l = 0; l < 32; l++) ws[w].push_back(S->terms[base + k * 32 + l]);
+  for (int r : order) {
+    int W = nwarps(r);
+    uint32_t b0 = S->rounds[3 * r], b1 = S->rounds[3 * r + 1];
+    for (uint32_t b = b0; b < b1; b++) {
+      int w = (int)((b - b0) % (uint32_t)W);
+      for (uint32_t row = S->brow[b]; row < S->brow[b + 1]; row++)
+        ws[w].insert(ws[w].end(), S->chunks + (size_t)row * 128, S->chunks + (size_t)(row + 1) * 128);
     }
   }
   hp.stream.clear();
   for (int w = 0; w < NW; w++) {
-    while ((int)ws[w].size() < 32 * 2 * RING) ws[w].insert(ws[w].end(), 32, 0u);   // never shorter than the ring (idle warps)
-    hp.warp_off[w] = (int)(hp.stream.size() / 32);
-    hp.warp_rows[w] = (int)(ws[w].size() / 32);
+    while ((int)ws[w].size() < 128 * 2 * RS) ws[w].insert(ws[w].end(), 128, 0u);   // idle warps only prefetch
+    hp.warp_off[w] = (int)(hp.stream.size() / 128);
+    hp.warp_rows[w] = (int)(ws[w].size() / 128);
     hp.stream.insert(hp.stream.end(), ws[w].begin(), ws[w].end());
   }
-  // a warp with no work at all never consumes: its padded stream is only prefetched
   hp.aw.resize(2 * (size_t)T->nreact);
   for (int r = 0; r < T->nreact; r++) encode_term(T->a_term + 4 * r, T->nreact, T->nspec, T->nlit, &hp.aw[2 * r]);
   hp.bw.resize(2 * (size_t)(T->nb > 0 ? T->nb : 1));
   for (int m = 0; m < T->nb; m++) encode_term(T->b_term + 4 * m, T->nreact, T->nspec, T->nlit, &hp.bw[2 * m]);
-  hp.diag.resize(T->nvar);
+  hp.diag.resize(T->nvar); hp.crow.resize(T->nvar + 1);
   for (int i = 0; i < T->nvar; i++) hp.diag[i] = (uint16_t)T->diag[i];
-  if (T->nspec + T->nlit + 1 >= 65536 || T->nreact + T->nlit >= 65535 || T->nnz >= 65536) return -1;
-  size_t bytes = sizeof(double) * ((size_t)NC * (D.nnz + D.nyg + D.nvar + D.nscr) + D.ncoef + (size_t)NW * NC);
-  bytes += sizeof(Slot) * NC;
-  bytes += sizeof(uint32_t) * (size_t)NW * RING * 32;
-  bytes += sizeof(uint16_t) * (2 * (size_t)D.nprog_pad + D.nvar);
-  hp.smem_bytes = (bytes + 15) & ~(size_t)15;
-  hp.NW = NW;
+  for (int i = 0; i <= T->nvar; i++) hp.crow[i] = (uint16_t)T->crow[i];
+  if (T->nspec + T->nlit + 1 >= 65536 || T->nreact + T->nlit >= 65535 || (T->nnz + 1) * 8 >= 65536) return -4;
+  int off = mech_id == GCKPP_MECH_FULLCHEM ? dyn_offset<fullchem_dims>() : dyn_offset<Hg_dims>();
+  auto take = [&](size_t bytes) { int o = off; off = (int)((off + bytes + 15) & ~(size_t)15); return o; };
+  hp.s_res = take(hp.resident.size() * 4);
+  hp.s_tpos = take(32 * 32 * 2);
+  hp.s_boff = take(hp.boff.size() * 2 + 2);
+  hp.s_dir = take(hp.dir.size() * 4);
+  hp.s_diag = take(hp.diag.size() * 2);
+  hp.s_crow = take(hp.crow.size() * 2);
+  hp.s_total = off;
   return 0;
 }
 
-template <int NW, int NA_IT, int NB_IT>
-static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, size_t smem, cudaStream_t s)
+template <class M>
+static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s)
 {
-  auto k = ros_smem_kernel<SMEM_NC, NW, NA_IT, NB_IT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto k = ros_smem_kernel<M>;
+  static int configured = 0;
+  if (configured < P.s_total) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.s_total);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = P.s_total;
   }
-  k<<<blocks, NW * 32, smem, s>>>(P, a);
+  k<<<blocks, NT, P.s_total, s>>>(P, a);
   return cudaGetLastError();
 }
 
-bool smem_kernel_supports(const gckpp_host_tables_t *T, int NW)
+cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s)
 {
-  const int NT = NW * 32;
-  if (T->nnz <= 0 || T->nspec > NT) return false;
-  int na = (T->nreact + NT - 1) / NT, nb = (T->nb + NT - 1) / NT;
-  if (NW == 12) return (na == 3 && nb == 5) || (na == 1 && nb == 1);
-  if (NW == 8) return (na == 5 && nb == 8) || (na == 1 && nb == 1);
-  return false;
-}
-
-cudaError_t launch_ros_smem(const SmemArgs &P, const RosArgs &a, int NW, int blocks, size_t smem, cudaStream_t s)
-{
-  const int NT = NW * 32;
-  int na = (P.D.nreact + NT - 1) / NT, nb = (P.D.nb + NT - 1) / NT;
-  if (NW == 12 && na == 3 && nb == 5) return launch_t<12, 3, 5>(P, a, blocks, smem, s);
-  if (NW == 12 && na == 1 && nb == 1) return launch_t<12, 1, 1>(P, a, blocks, smem, s);
-  if (NW == 8 && na == 5 && nb == 8) return launch_t<8, 5, 8>(P, a, blocks, smem, s);
-  if (NW == 8 && na == 1 && nb == 1) return launch_t<8, 1, 1>(P, a, blocks, smem, s);
+  if (mech_id == GCKPP_MECH_FULLCHEM) return launch_t<fullchem_dims>(P, a, blocks, s);
+  if (mech_id == GCKPP_MECH_HG) return launch_t<Hg_dims>(P, a, blocks, s);
   return cudaErrorInvalidConfiguration;
 }

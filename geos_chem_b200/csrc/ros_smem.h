@@ -5,40 +5,38 @@
 #include <vector>
 #include "ros_common.cuh"
 
-#define SMEM_NC 3          // cells integrated in lock step by one thread block
-#define SMEM_MAX_WARPS 16
-
-struct SmemDims {
-  int nvar, nspec, nreact, nnz, nb, nlit;
-  int nyg;                 // nspec + nlit + 1: [VAR, FIX, literal pool, 1.0]
-  int nscr;                // max(nreact, nb)
-  int ncoef;
-  int n_lu, n_fwd, n_bwd;  // rounds per phase
-  int nprog, nprog_pad;    // rounds of one attempt
-};
+#define SMEM_NC 2          // cells integrated in lock step by one thread block
+#define SMEM_NW 12         // warps per block
+#define SMEM_RS 6          // ring slots (512-byte chunk rows) per warp for the streamed tables
 
 struct SmemArgs {
-  SmemDims D;
-  const uint32_t *stream;                 // per-warp table streams, rows of 32 words
-  int warp_off[SMEM_MAX_WARPS];           // first row of each warp's stream
-  int warp_rows[SMEM_MAX_WARPS];          // cyclic length of each warp's stream (rows per attempt)
-  const uint16_t *prog_nb;                // [nprog] bundles of the round | 0x8000 for LU division rounds
-  const uint16_t *prog_P;                 // [nprog] warps that synchronise after the round
-  const uint16_t *diag;                   // [nvar] LU_DIAG
+  // streamed tables (vdot, jvs, lu rounds): per-warp chunk rows in consumption order, cyclic per attempt
+  const uint4 *stream;
+  int warp_off[SMEM_NW], warp_rows[SMEM_NW];
+  // resident tables (fwd, bwd rounds): copied to shared memory at kernel start
+  const uint4 *resident; int res_rows;
+  const uint16_t *boff; int nresb;        // first chunk row of every resident bundle
+  const uint32_t *dir; int ndir;          // round directory: nb | W<<12 | P<<16 | div<<20 | first resident bundle<<21
+  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd;
+  const uint16_t *tpos;                   // [32][32]
+  const uint16_t *diag, *crow;            // [nvar], [nvar+1]
   const uint32_t *aw, *bw;                // [nreact][2], [nb][2] encoded rate / partial-derivative terms
   const double *coefs;                    // [ncoef] stoichiometric coefficients (signed)
   const double *lit;                      // [nlit] literal pool
+  double *rcs;                            // per-block scratch: rate constants in item order, [blocks][NC][items]
+  // byte offsets of the runtime-sized shared-memory regions
+  int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
 };
 
 struct SmemHostPlan {
-  SmemDims D;
-  int NW;
-  size_t smem_bytes;
-  int warp_off[SMEM_MAX_WARPS], warp_rows[SMEM_MAX_WARPS];
-  std::vector<uint32_t> stream, aw, bw;
-  std::vector<uint16_t> prog_nb, prog_P, diag;
+  int warp_off[SMEM_NW], warp_rows[SMEM_NW];
+  std::vector<uint32_t> stream, resident, dir, aw, bw;
+  std::vector<uint16_t> boff, diag, crow;
+  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd;
+  int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
 };
 
-bool smem_kernel_supports(const gckpp_host_tables_t *T, int NW);
-int smem_plan_build(const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, int NW, SmemHostPlan &hp);
-cudaError_t launch_ros_smem(const SmemArgs &P, const RosArgs &a, int NW, int blocks, size_t smem, cudaStream_t s);
+bool smem_kernel_supports(int mech_id);
+int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, SmemHostPlan &hp);
+size_t smem_rcs_doubles_per_block(int mech_id);
+cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s);

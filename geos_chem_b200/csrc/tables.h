@@ -18,10 +18,13 @@ struct gckpp_host_tables_t {
 
 // Round/bundle schedules of the shared-memory kernel (kppgen/sched.py documents the encoding).
 struct gckpp_sched_tables_t {
-  int nterms, nlanes, nbundles, nrounds;
-  const uint32_t *terms, *lanes, *bundles /* [nbundles][2] */, *rounds /* [nrounds][3]: first, last+1, kind */;
+  int nrows, nbundles, nrounds;
+  const uint32_t *chunks /* [nrows][32][4] */, *brow /* [nbundles+1] first chunk row of a bundle */,
+      *rounds /* [nrounds][3]: first bundle, last+1, kind (bit 4: LU division round) */;
   int phase[12];                                       // round ranges of vdot, jvs, lu, scale, fwd, bwd
   const double *coefs; int ncoef;
+  const uint16_t *tpos;                                // [32][32] tposT[j][i] = position of G(h+i,h+j) or 0xFFFF
+  int head, tail;
 };
 
 // Device copy: same fields, device pointers.

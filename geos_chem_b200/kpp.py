@@ -64,6 +64,7 @@ def load_library(path=None):
     L.gckpp_gpu_set_stream.argtypes = [vp, vp]
     L.gckpp_gpu_fp64_peak.argtypes = [C.c_int, dp, dp]
     L.gckpp_gpu_last_error.restype = C.c_char_p
+    L.gckpp_gpu_plan_info.argtypes = [C.c_int, ip]
     _lib = L
     return L
 
@@ -72,7 +73,17 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
            "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
            "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error", "gckpp_gpu_set_stream",
-           "gckpp_gpu_fp64_peak"]
+           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info"]
+
+
+def plan_info(mech):
+    """static plan of the shared-memory kernel (host-only query)"""
+    L = load_library()
+    d = (C.c_int32 * 8)()
+    if L.gckpp_gpu_plan_info(MECH_ID[mech], d) != 0:
+        raise KppError(L.gckpp_gpu_last_error().decode())
+    return dict(zip(("smem_bytes", "stream_rows", "resident_rows", "rounds", "n_lu", "n_fwd", "n_bwd", "cells_per_block"),
+                    (int(x) for x in d)))
 
 
 def mech_dims(mech):

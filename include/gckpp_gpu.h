@@ -143,6 +143,12 @@ int gckpp_gpu_fp64_peak(int device, double *tflops_out, double *ms_out);
  * stats[9] device time of the whole call (rate constants + integration + retry) [ms]. */
 int gckpp_gpu_last_stats(gckpp_gpu_handle_t *handle, double *stats /* [16] */);
 
+/* Host-only description of the shared-memory kernel's static plan for a mechanism (no GPU needed):
+ * info[0] dynamic shared memory per block [bytes], info[1] streamed table rows (512 B) per attempt,
+ * info[2] resident table rows, info[3] rounds in the directory, info[4..6] LU / forward / backward
+ * rounds, info[7] cells per block. */
+int gckpp_gpu_plan_info(int mech_id, int32_t *info /* [8] */);
+
 /* Last error text (thread-local). */
 const char *gckpp_gpu_last_error(void);
 

@@ -60,6 +60,8 @@ def test_schedule_matches_oracle(mech):
     H, gam = 300.0, 0.5
     ghinv = 1.0 / (H * gam)
     G = s.emulate_jac(B, ghinv)
+    assert G[-1] == 0.0          # the zero slot the padding terms point at
+    G = G[:-1]
     Gref = -jvs_o.copy()
     Gref[np.array(m.lu_diag)] += ghinv
     np.testing.assert_allclose(G, Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
@@ -68,8 +70,10 @@ def test_schedule_matches_oracle(mech):
     assert ier == 0
     b = rng.standard_normal(m.nvar) * np.abs(vdot_o).max()
     x_o = o.solve(mech, lu_o, b)
-    Glu = s.emulate_lu(Gref.copy())
+    Glu = s.emulate_lu(np.append(Gref, 0.0))
     x = s.emulate_solve(Glu, b.copy())
+    assert Glu[-1] == 0.0
+    Glu = Glu[:-1]
     np.testing.assert_allclose(x, x_o, rtol=1e-9, atol=1e-12 * np.abs(x_o).max())
     # L multipliers are the reference's; U rows are the reference's divided by the pivot
     d = np.array(m.lu_diag)

@@ -14,7 +14,6 @@ o = Oracle()
 
 def run(kernel, *a, warps=12, **k):
     s.set_option("kernel", kernel)
-    s.set_option("warps", warps)
     t0 = time.time()
     out = s.Integrate(*a, **k)
     return out, time.time() - t0, s.last_stats()
@@ -50,8 +49,8 @@ if stage == "full":
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     conc, temp, numden, h2o, photol, khet, hs = map(t, (g["conc"], g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"], g["hstart"]))
-    for warps in (12, 8):
-        s.set_option("kernel", 1); s.set_option("warps", warps)
+    for warps in (12,):
+        s.set_option("kernel", 1)
         for it in range(2):
             torch.cuda.synchronize(); t0 = time.time()
             out = s.Integrate(0.0, 1200.0, conc, None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs, TEMP=temp, NUMDEN=numden, H2O=h2o, PHOTOL=photol, khet=khet)
