@@ -441,7 +441,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
 // The shared-memory kernel implements the method GEOS-Chem selects (Rodas3, ICNTRL(3) = 0 or 4).
 static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
-  if (h->opt_kernel != 1) return false;      // default: table-driven kernel until the shared-memory kernel is the faster one
+  if (h->opt_kernel == 0) return false;      // "kernel"=0 forces the table-driven, reference-order kernel
   if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->mech_id)) return false;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
   if (d.o.Tstart == d.o.Tend) return false;

@@ -60,7 +60,10 @@ int gckpp_gpu_finalize(gckpp_gpu_handle_t *handle);
 /* Options (integer-valued):
  *   "retry"      1 = on IERR<0 redo the cell once with Hstart=0 from the saved
  *                concentrations (Do_FullChem's policy, fullchem_mod.F90:1138-1162); default 0
- *   "kernel"     0 = table-driven kernels, 1 = mechanism-specialised kernels (default: best available)
+ *   "kernel"     0 = table-driven one-cell-per-lane kernel that keeps the reference's operation order
+ *                (bit-identical step sequences with the CPU restatement, any ICNTRL(3) method);
+ *                1 = shared-memory-resident Rodas3 kernel (default for fullchem and Hg with
+ *                ICNTRL(3) = 0 or 4; sums re-associated, FMA contraction, rounding-level differences)
  *   "sort"       1 = visit cells in descending previous-step cost (hstart ascending); default 0
  */
 int gckpp_gpu_set_option(gckpp_gpu_handle_t *handle, const char *key, int value);

@@ -55,3 +55,15 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "kpp_oracle" not in txt and "libkpp_oracle" not in txt, os.path.join(dp, f)
+
+
+def test_smem_kernel_plan_fits_b200(lib):
+    """host-only query of the shared-memory kernel's static plan: it must fit one B200 SM (227 KB opt-in)"""
+    from geos_chem_b200 import kpp
+    for mech in ("fullchem", "Hg"):
+        p = kpp.plan_info(mech)
+        assert 0 < p["smem_bytes"] + 1024 <= 227 * 1024, p
+        assert p["cells_per_block"] >= 1
+    p = kpp.plan_info("fullchem")
+    # head/tail split of the elimination DAG: 21 LU rounds and 19 sweep rounds instead of 72 + 68 levels
+    assert (p["n_lu"], p["n_fwd"], p["n_bwd"]) == (21, 10, 9)

@@ -1,11 +1,14 @@
 """GPU parity tests proper: every call goes through the C ABI (libgckpp_b200.so) and is compared
-with the CPU oracle on the same inputs.  Tolerances:
+with the CPU oracle on the same inputs.  Two integrator kernels are covered: "smem" (the default,
+shared-memory-resident Rodas3 kernel; re-associated sums + FMA) and "table" (option kernel=0, the
+table-driven kernel in the reference's operation order).  Tolerances:
   * single routines (Fun, Jac_SP, KppDecomp, KppSolve) with the table-driven kernel: bit-exact
     (same operation order, no FMA contraction; integer/IEEE +,-,*,/ only)
   * Update_RCONST: relative 1e-10 worst case, 1e-15 median (CUDA vs glibc exp/pow/log10 differ in
     the last ulps and some laws cancel)
-  * Integrate: north-star bar -- every species above 1e3 molec/cm3 within 1e-4 relative,
-    and identical step counts per cell
+  * Integrate: north-star bar -- every species above 1e3 molec/cm3 within 1e-4 relative (both
+    kernels); step counts per cell identical for the table kernel, and reported (allowed to differ in
+    at most 0.1 % of the cells, each still within the 1e-4 bar) for the smem kernel
 """
 import numpy as np
 import pytest
@@ -73,9 +76,14 @@ def test_update_rconst_vs_oracle(solver, oracle):
     assert np.median(err[ro != 0]) < 1e-15
 
 
-def test_integrate_fixture_replicated(solver, fx):
+KERNELS = {"smem": 1, "table": 0}
+
+
+@pytest.mark.parametrize("kernel", ["smem", "table"])
+def test_integrate_fixture_replicated(solver, fx, kernel):
     """config 1: the Beijing cell, replicated; the 3-D model's own answer is 12 steps, Hexit 497.8023"""
-    r = grid.replicate_fixture(96, fx)
+    solver.set_option("kernel", KERNELS[kernel])
+    r = grid.replicate_fixture(97, fx)     # odd count: the last block of the smem kernel runs half empty
     c, ist, rst, ierr, nf = solver.Integrate(0.0, r["dt"], r["conc"], r["rconst"], r["atol"], r["rtol"],
                                              r["icntrl"], r["rcntrl"])
     assert (ierr == 1).all()
@@ -92,8 +100,10 @@ def _parity(c, co, floor=1e3):
     return rel
 
 
+@pytest.mark.parametrize("kernel", ["smem", "table"])
 @pytest.mark.parametrize("hstart", ["warm", "cold"])
-def test_integrate_grid_sample_vs_oracle(solver, oracle, hstart):
+def test_integrate_grid_sample_vs_oracle(solver, oracle, hstart, kernel):
+    solver.set_option("kernel", KERNELS[kernel])
     g = grid.make_grid("4x5", hstart=hstart)
     rng = np.random.default_rng(7)
     idx = np.sort(rng.choice(g["conc"].shape[1], 3000, replace=False))
@@ -109,9 +119,59 @@ def test_integrate_grid_sample_vs_oracle(solver, oracle, hstart):
     rel = _parity(c, co)
     print("cells with different step sequences:", int((~same_steps).sum()), "max rel err:", rel.max())
     assert rel.max() <= 1e-4
-    assert same_steps.all()
+    hist = lambda a: np.bincount(a, minlength=64)[:64].tolist()
+    print("Nstp histogram  gpu:", hist(ist[kpp.Nstp]), "\n                cpu:", hist(isto[kpp.Nstp]))
+    if kernel == "table":
+        assert same_steps.all()
+    else:
+        assert (~same_steps).sum() <= max(1, conc.shape[1] // 1000)
     # Texit/Hexit/Hnew: only the pow() in the step-size controller differs (CUDA vs glibc, last ulp),
     # which the stiff solves amplify a little
-    hd = np.abs(rst[:3] - rsto[:3]) / np.maximum(np.abs(rsto[:3]), 1e-300)
+    hd = np.abs(rst[:3] - rsto[:3])[:, same_steps] / np.maximum(np.abs(rsto[:3])[:, same_steps], 1e-300)
     print("max rel diff of Texit/Hexit/Hnew:", hd.max())
     assert hd.max() < 1e-6
+
+
+def test_integrate_active_mask_and_retry(solver, oracle):
+    """cells outside the chemistry grid are copied through with ierr 0; the retry option re-runs failures"""
+    solver.set_option("kernel", 1)
+    g = grid.make_grid("4x5", limit=1500)
+    rng = np.random.default_rng(11)
+    active = (rng.uniform(size=1500) < 0.7).astype(np.uint8)
+    c, ist, rst, ierr, nf = solver.Integrate(0.0, 1200.0, g["conc"], None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"],
+                                             hstart=g["hstart"], active=active, TEMP=g["temp"], NUMDEN=g["numden"],
+                                             H2O=g["h2o"], PHOTOL=g["photol"], khet=g["khet"])
+    off = active == 0
+    assert (ierr[off] == 0).all() and (ierr[~off] == 1).all()
+    assert np.array_equal(c[:, off], g["conc"][:, off]) and (ist[:, off] == 0).all()
+    rc = oracle.update_rconst("fullchem", g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"])
+    on = np.flatnonzero(~off)[:200]
+    co, isto, _, _ = oracle.integrate("fullchem", 0.0, 1200.0, np.ascontiguousarray(g["conc"][:, on]),
+                                      np.ascontiguousarray(rc[:, on]), g["atol"], g["rtol"], g["icntrl"], g["rcntrl"],
+                                      hstart=g["hstart"][on])
+    assert _parity(c[:, on], co).max() <= 1e-4
+
+
+def test_hg_mechanism_vs_oracle(lib, oracle):
+    """small-mechanism path (config 5): Hg, 32 variable species, Rodas3; both kernels against the oracle.
+    Parity is unpinned by the reference (no Hg fixture exists); inputs are log-uniform and documented here."""
+    s = kpp.KppSolver("Hg", device=0, max_cells=4096)
+    d = s.dims
+    rng = np.random.default_rng(20190701)
+    n = 1001
+    conc = 10.0 ** rng.uniform(2, 8, size=(d["nspec"], n))
+    rconst = 10.0 ** rng.uniform(-16, -11, size=(d["nreact"], n))
+    atol, rtol = np.full(d["nvar"], 1e-2), np.full(d["nvar"], 1e-2)
+    icntrl = np.zeros(20, np.int32); icntrl[[0, 2, 6, 14]] = [1, 4, 1, -1]
+    rcntrl = np.zeros(20)
+    co, isto, rsto, ierro = oracle.integrate("Hg", 0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
+    for kernel in ("smem", "table"):
+        s.set_option("kernel", KERNELS[kernel])
+        c, ist, rst, ierr, _ = s.Integrate(0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
+        assert np.array_equal(ierr, ierro)
+        rel = _parity(c, co)
+        same = np.all(ist == isto, axis=0)
+        print("Hg %s: max rel %.3e, cells with different steps %d" % (kernel, rel.max(), int((~same).sum())))
+        assert rel.max() <= 1e-4
+        assert same.all() if kernel == "table" else (~same).sum() <= 2
+    s.close()
