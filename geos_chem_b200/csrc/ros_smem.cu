@@ -826,7 +826,11 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   }
   hp.stream.clear();
   for (int w = 0; w < NW; w++) {
-    while ((int)ws[w].size() < 128 * 2 * RS) ws[w].insert(ws[w].end(), 128, 0u);   // idle warps only prefetch
+    // The ring needs a stream of at least 2*RS rows.  A short stream is repeated whole (it is cyclic, so
+    // a multiple of the period reads the same); a warp without any work only ever prefetches zeros.
+    if (ws[w].empty()) ws[w].assign((size_t)128 * 2 * RS, 0u);
+    const std::vector<uint32_t> period = ws[w];
+    while ((int)ws[w].size() < 128 * 2 * RS) ws[w].insert(ws[w].end(), period.begin(), period.end());
     hp.warp_off[w] = (int)(hp.stream.size() / 128);
     hp.warp_rows[w] = (int)(ws[w].size() / 128);
     hp.stream.insert(hp.stream.end(), ws[w].begin(), ws[w].end());
