@@ -27,7 +27,9 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_ATTEMPT = 126572.0   # one Rodas3 attempt (LU + 4 solves + 2 Fun + vector ops)
 FLOP_PER_ACCEPT = 23235.0     # + 1 Fun + 1 Jac per accepted step
-ALG_BYTES_PER_CELL = 7000.0   # C in/out + met/PHOTOL/khet + status when K1 is on the device
+# algorithmic HBM bytes of the integrator kernel per cell: C in 356*8 + RCONST 1058*8 (written by the
+# Update_RCONST kernel, read once) + C out 356*8 + ISTATUS 32 + RSTATUS 32 + IERR 4 + hstart 8 = 14236
+ALG_BYTES_PER_CELL = 14236.0
 
 
 def peaks():
@@ -271,7 +273,7 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_cell", 0.0) * ncell or None   # ncu capture, scaled per cell
         h2d = sum(int(v.numel() * v.element_size()) for v in host.values())
         d2h = sum(int(v.nbytes) for v in h_out.values())
         line = {
