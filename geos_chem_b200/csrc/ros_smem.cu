@@ -591,6 +591,23 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         // The tables do not depend on the data, so the directory entry and the first two chunks of
         // the NEXT round are fetched before waiting on the barrier of the current one.
         const int n_tot = P.n_fwd + P.n_bwd;
+        auto tails = [&]() {
+          if (warp < NC) tail_fwd<M>(G + warp * L::GS, X + warp * N, tposT, lane);
+          __syncthreads();
+          if (warp < NC) {
+            tail_bwd<M>(G + warp * L::GS, X + warp * N, tposT, diag, lane);
+          } else {
+            for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
+              const int dp = diag[i];
+#pragma unroll
+              for (int c = 0; c < NC; c++) X[c * N + i] *= G[c * L::GS + dp];
+            }
+          }
+          __syncthreads();
+          PROF(11);
+        };
+        PROF(6);
+#if SMEM_SWEEP_RESIDENT
         auto prefetch = [&](int r, unsigned &d, PreReader &pr) {
           d = 0; pr.n = 0; pr.p = RES + lane;
           if (r < n_tot) {
@@ -602,25 +619,10 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           }
         };
         unsigned dn; PreReader pn;
-        PROF(6);
         prefetch(0, dn, pn);
 #pragma unroll 1
         for (int r = 0;; r++) {
-          if (r == P.n_fwd) {
-            if (warp < NC) tail_fwd<M>(G + warp * L::GS, X + warp * N, tposT, lane);
-            __syncthreads();
-            if (warp < NC) {
-              tail_bwd<M>(G + warp * L::GS, X + warp * N, tposT, diag, lane);
-            } else {
-              for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
-                const int dp = diag[i];
-#pragma unroll
-                for (int c = 0; c < NC; c++) X[c * N + i] *= G[c * L::GS + dp];
-              }
-            }
-            __syncthreads();
-            PROF(11);
-          }
+          if (r == P.n_fwd) tails();
           if (r == n_tot) break;
           const unsigned d = dn;
           const int nb = d & 0xfff, W = (d >> 12) & 15, bf = d >> 21;
@@ -638,6 +640,18 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           round_barrier((d >> 16) & 15, warp);
           PROF(10);
         }
+#else
+#pragma unroll 1
+        for (int r = 0;; r++) {
+          if (r == P.n_fwd) tails();
+          if (r == n_tot) break;
+          const unsigned d = dir[P.o_fwd + r];
+          stream_round(std::integral_constant<int, OP_SOLVE>(), d);
+          PROF(8);
+          round_barrier((d >> 16) & 15, warp);
+          PROF(10);
+        }
+#endif
         if (tid < N) {
 #pragma unroll
           for (int c = 0; c < NC; c++) {
@@ -788,7 +802,7 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   // resident bundles: all bundles of the fwd and bwd rounds, in directory order
   hp.resident.clear(); hp.boff.clear();
   std::vector<int> bfirst(dr.size(), 0);
-  for (size_t i = (size_t)hp.o_fwd; i < dr.size(); i++) {
+  for (size_t i = (size_t)hp.o_fwd; SMEM_SWEEP_RESIDENT && i < dr.size(); i++) {
     int r = dr[i];
     bfirst[i] = (int)hp.boff.size();
     for (uint32_t b = S->rounds[3 * r]; b < S->rounds[3 * r + 1]; b++) {
@@ -809,11 +823,19 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
     uint32_t div = (S->rounds[3 * r + 2] & 0x10) ? 1u : 0u;
     hp.dir[i] = (uint32_t)nb | ((uint32_t)W << 12) | ((uint32_t)Pb << 16) | (div << 20) | ((uint32_t)bfirst[i] << 21);
   }
-  // per-warp streams: vdot, jvs, lu rounds, vdot, vdot (one Rodas3 attempt)
+  // per-warp streams in the order one Rodas3 attempt consumes them: vdot, jvs, lu rounds, [sweeps x2], vdot,
+  // [sweeps], vdot, [sweeps]  (the sweeps only when their tables are not resident)
   std::vector<int> order;
+  auto push_sweeps = [&]() {
+    if (SMEM_SWEEP_RESIDENT) return;
+    for (int r = r0(4); r < r1(4); r++) order.push_back(r);
+    for (int r = r0(5); r < r1(5); r++) order.push_back(r);
+  };
   order.push_back(r0(0)); order.push_back(r0(1));
   for (int r = r0(2); r < r1(2); r++) order.push_back(r);
-  order.push_back(r0(0)); order.push_back(r0(0));
+  push_sweeps(); push_sweeps();
+  order.push_back(r0(0)); push_sweeps();
+  order.push_back(r0(0)); push_sweeps();
   std::vector<std::vector<uint32_t>> ws(NW);
   for (int r : order) {
     int W = nwarps(r);

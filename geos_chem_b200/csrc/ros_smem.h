@@ -5,9 +5,20 @@
 #include <vector>
 #include "ros_common.cuh"
 
-#define SMEM_NC 2          // cells integrated in lock step by one thread block
+#ifndef SMEM_NC
+#define SMEM_NC 3          // cells integrated in lock step by one thread block
+#endif
 #define SMEM_NW 12         // warps per block
+// With 2 cells per block the tables of the triangular sweeps (used 4x per attempt) stay resident in shared
+// memory and the ring is 6 slots deep; with 3 cells the space goes to the third matrix and the sweep tables
+// are streamed like the others through a 4-slot ring.
+#if SMEM_NC <= 2
+#define SMEM_SWEEP_RESIDENT 1
 #define SMEM_RS 6          // ring slots (512-byte chunk rows) per warp for the streamed tables
+#else
+#define SMEM_SWEEP_RESIDENT 0
+#define SMEM_RS 4
+#endif
 
 struct SmemArgs {
   // streamed tables (vdot, jvs, lu rounds): per-warp chunk rows in consumption order, cyclic per attempt
