@@ -113,12 +113,13 @@ def run_reference(args, rank, world):
     sub = lambda a: np.ascontiguousarray(a[..., idx])
     conc, hs = sub(g["conc"]), sub(g["hstart"])
     temp, numden, h2o, photol, khet = map(sub, (g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"]))
-    cores = os.cpu_count()
+    cores = host_cores()      # explicit: torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        rc = o.update_rconst("fullchem", temp, numden, h2o, photol, khet)
-        o.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs)
+        rc = o.update_rconst("fullchem", temp, numden, h2o, photol, khet, nthreads=cores)
+        o.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs,
+                    nthreads=cores)
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     T = sum(times)
@@ -133,6 +134,13 @@ def run_reference(args, rank, world):
                              "note": "C/OpenMP restatement of the reference algorithm, not gfortran/ifort output"},
             "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
 
 
 def workload_name(args, world):
@@ -326,13 +334,15 @@ def cpu_baseline(args, g):
     conc, hs = sub(g["conc"]), sub(g["hstart"])
     temp, numden, h2o, photol, khet = map(sub, (g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"]))
     best = None
+    cores = host_cores()
     for _ in range(2):
         t0 = time.perf_counter()
-        rc = o.update_rconst("fullchem", temp, numden, h2o, photol, khet)
-        o.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs)
+        rc = o.update_rconst("fullchem", temp, numden, h2o, photol, khet, nthreads=cores)
+        o.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs,
+                    nthreads=cores)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": len(idx) / best, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": len(idx) / best, "unit": "cells/s", "cores": cores, "kind": "port",
             "sample": "every %d-th cell of the workload (%d cells), best of 2" % (stride, len(idx)),
             "note": "C/OpenMP (schedule(dynamic,24)) restatement of the reference algorithm, not gfortran/ifort output"}
 
