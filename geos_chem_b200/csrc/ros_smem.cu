@@ -148,10 +148,18 @@ __device__ __forceinline__ void round_barrier(int P, int warp)
 }
 
 // One bundle: every lane applies its terms to all NC cells.
+#ifdef SMEM_PROFILE
+#define BPROF(i) do { if (bp) { long long t_ = clock64(); bp[i] += t_ - bt_; bt_ = t_; } } while (0)
+#else
+#define BPROF(i) do { } while (0)
+#endif
 template <class M, int OP, class RD>
-__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot)
+__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot, long long *bp = nullptr)
 {
   using L = Lay<M>;
+#ifdef SMEM_PROFILE
+  long long bt_ = clock64();
+#endif
   double *G = reinterpret_cast<double *>(smem + L::oG);
   double *X = reinterpret_cast<double *>(smem + L::oX);
   const uint4 c0 = rd.next();
@@ -187,15 +195,18 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
     }
     return;
   }
+  BPROF(12);
   term(c0.y); term(c0.z); term(c0.w);
   for (int k0 = 3; k0 < maxlen; k0 += 4) {
     const uint4 cc = rd.next();
     term(cc.x); term(cc.y); term(cc.z); term(cc.w);
   }
+  BPROF(13);
   for (int s = 0; s < lg; s++) {
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] += __shfl_down_sync(FULLMASK, acc[c], 1 << s);
   }
+  BPROF(14);
   if ((lw >> 28) & 1) {
     if (OP == OP_VDOT) {
 #pragma unroll
@@ -211,6 +222,7 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
       for (int c = 0; c < NC; c++) X[c * M::NVAR + row] -= acc[c];
     }
   }
+  BPROF(15);
 }
 
 // ---- tail block: one warp per cell ---------------------------------------------------------------------
@@ -646,7 +658,15 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           if (r == P.n_fwd) tails();
           if (r == n_tot) break;
           const unsigned d = dir[P.o_fwd + r];
+#ifdef SMEM_PROFILE
+          {
+            const int nb = d & 0xfff, W = (d >> 12) & 15;
+            if (warp < W)
+              for (int b = warp; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, (tid == 0 && blockIdx.x == 0) ? pacc_ : nullptr);
+          }
+#else
           stream_round(std::integral_constant<int, OP_SOLVE>(), d);
+#endif
           PROF(8);
           round_barrier((d >> 16) & 15, warp);
           PROF(10);

@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgckpp_b200.so")
+LIB_PATH = os.environ.get("GCKPP_B200_LIB") or os.path.join(_HERE, "libgckpp_b200.so")
 MECH_ID = {"fullchem": 0, "Hg": 1, "carbon": 2}
 
 # ISTATUS / RSTATUS slots (gckpp_Integrator.F90:57-63)

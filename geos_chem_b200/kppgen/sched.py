@@ -40,8 +40,9 @@ A round uses W = min(NW, bundles) warps; bundle b of the round goes to warp b % 
 """
 import numpy as np
 
-LMAX = 8          # target number of terms per lane before a row is split over more lanes
-SOLVE_LMAX = 7    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
+import os as _os
+LMAX = int(_os.environ.get('GCKPP_LMAX', 8))          # target number of terms per lane before a row is split over more lanes
+SOLVE_LMAX = int(_os.environ.get('GCKPP_SOLVE_LMAX', 7))    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
 TAIL = 32         # tail block size (one lane per tail row)
 NONE = 0xFFFF
 
