@@ -154,7 +154,11 @@ __device__ __forceinline__ void round_barrier(int P, int warp)
 #define BPROF(i) do { } while (0)
 #endif
 template <class M, int OP, class RD>
+#ifdef SMEM_PROFILE
 __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot, long long *bp = nullptr)
+#else
+__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot)
+#endif
 {
   using L = Lay<M>;
 #ifdef SMEM_PROFILE

@@ -1,2 +1,2 @@
 #!/bin/bash
-( GCKPP_PROFILE=1 timeout 120 python tools/smem_one.py 444 ) 2>&1 | tail -3
+timeout 200 python tools/variant_bench.py own 2>&1 | tail -2
