@@ -98,7 +98,7 @@ struct gckpp_gpu_handle {
   int sm_ready = 0, sm_blocks_cap = 0;
   SmemHostPlan plan;
   SmemArgs sargs{};
-  DevBuf sm_rcs, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
+  DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
   double stats[16]{};
 };
@@ -207,7 +207,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
-                    &h->sm_rcs, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -432,6 +432,8 @@ static int prepare_smem(gckpp_gpu_handle *h)
   A.lit = h->M.lit;
   if (h->sm_rcs.ensure(sizeof(double) * smem_rcs_doubles_per_block(h->mech_id) * (size_t)h->sm_count)) return fail(-1002, "out of device memory");
   A.rcs = h->sm_rcs.as<double>();
+  if (h->sm_scr.ensure(sizeof(double) * smem_scr_doubles_per_block(h->mech_id) * (size_t)h->sm_count)) return fail(-1002, "out of device memory");
+  A.scr = h->sm_scr.as<double>();
   A.s_res = p.s_res; A.s_tpos = p.s_tpos; A.s_boff = p.s_boff; A.s_dir = p.s_dir; A.s_diag = p.s_diag; A.s_crow = p.s_crow;
   A.s_total = p.s_total;
   h->sm_ready = 1;

@@ -82,7 +82,7 @@ struct Lay {
   static constexpr int oYG = oG + NC * GS * 8;
   static constexpr int oX = oYG + NC * NYG * 8;
   static constexpr int oSCR = oX + NC * M::NVAR * 8;
-  static constexpr int oCOEF = oSCR + NC * NSCR * 8;
+  static constexpr int oCOEF = oSCR + (SMEM_SCR_GLOBAL ? 0 : NC * NSCR * 8);
   static constexpr int oRED = oCOEF + M::NCOEF * 8;
   static constexpr int oSLOT = oRED + NW * NC * 8;
   static constexpr int oRING = align16(oSLOT + NC * (int)sizeof(Slot));
@@ -155,9 +155,9 @@ __device__ __forceinline__ void round_barrier(int P, int warp)
 #endif
 template <class M, int OP, class RD>
 #ifdef SMEM_PROFILE
-__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot, long long *bp = nullptr)
+__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot, const double *scrg, long long *bp = nullptr)
 #else
-__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot)
+__device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Slot *slot, const double *scrg)
 #endif
 {
   using L = Lay<M>;
@@ -181,8 +181,13 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
     const unsigned hi = w >> 16, lo = w & 0xffffu;
     if (OP == OP_VDOT || OP == OP_JVS) {
       const double cf = ld(Cb, hi);
+#if SMEM_SCR_GLOBAL
+#pragma unroll
+      for (int c = 0; c < NC; c++) acc[c] = fma(cf, __ldcg(scrg + c * L::NSCR + (lo >> 3)), acc[c]);
+#else
 #pragma unroll
       for (int c = 0; c < NC; c++) acc[c] = fma(cf, ld(Sb + c * L::NSCR * 8, lo), acc[c]);
+#endif
     } else if (OP == OP_LUUPD) {
 #pragma unroll
       for (int c = 0; c < NC; c++) acc[c] = fma(ld(Gb + c * L::GS * 8, hi), ld(Gb + c * L::GS * 8, lo), acc[c]);
@@ -327,7 +332,11 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   double *G = reinterpret_cast<double *>(smem + L::oG);            // [NC][NNZ+1]
   double *Yg = reinterpret_cast<double *>(smem + L::oYG);          // [NC][NYG] state under evaluation + literals + 1.0
   double *X = reinterpret_cast<double *>(smem + L::oX);            // [NC][NVAR] right-hand side / solution
+#if SMEM_SCR_GLOBAL
+  double *SCR = P.scr + (size_t)blockIdx.x * NC * L::NSCR;         // [NC][NSCR] A(r) or B(m), per-block global scratch
+#else
   double *SCR = reinterpret_cast<double *>(smem + L::oSCR);        // [NC][NSCR] A(r) or B(m)
+#endif
   double *COEF = reinterpret_cast<double *>(smem + L::oCOEF);
   double *RED = reinterpret_cast<double *>(smem + L::oRED);        // [NW][NC]
   Slot *slot = reinterpret_cast<Slot *>(smem + L::oSLOT);          // [NC]
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   auto stream_round = [&](auto opc, unsigned d) {
     const int nb = d & 0xfff, W = (d >> 12) & 15;
     if (warp < W)
-      for (int b = warp; b < nb; b += W) run_bundle<M, decltype(opc)::value>(rd, smem, slot);
+      for (int b = warp; b < nb; b += W) run_bundle<M, decltype(opc)::value>(rd, smem, slot, SCR);
   };
 
   for (;;) {
@@ -643,11 +652,11 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           const unsigned d = dn;
           const int nb = d & 0xfff, W = (d >> 12) & 15, bf = d >> 21;
           if (warp < W) {
-            run_bundle<M, OP_SOLVE>(pn, smem, slot);
+            run_bundle<M, OP_SOLVE>(pn, smem, slot, SCR);
             for (int b = warp + W; b < nb; b += W) {       // only if a round has more bundles than warps
               ResReader rr;
               rr.p = RES + (size_t)boff[bf + b] * 32 + lane;
-              run_bundle<M, OP_SOLVE>(rr, smem, slot);
+              run_bundle<M, OP_SOLVE>(rr, smem, slot, SCR);
             }
           }
           PROF(8);
@@ -666,7 +675,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           {
             const int nb = d & 0xfff, W = (d >> 12) & 15;
             if (warp < W)
-              for (int b = warp; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, (tid == 0 && blockIdx.x == 0) ? pacc_ : nullptr);
+              for (int b = warp; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR, (tid == 0 && blockIdx.x == 0) ? pacc_ : nullptr);
           }
 #else
           stream_round(std::integral_constant<int, OP_SOLVE>(), d);
@@ -796,6 +805,11 @@ template <class M> static bool dims_match(const gckpp_host_tables_t *T, const gc
          T->nlit == M::NLIT && S->ncoef == M::NCOEF && S->tail == M::TAIL && S->head == M::HEAD;
 }
 
+template <class M> static size_t scr_doubles() { return (size_t)NC * Lay<M>::NSCR; }
+size_t smem_scr_doubles_per_block(int mech_id)
+{
+  return mech_id == GCKPP_MECH_FULLCHEM ? scr_doubles<fullchem_dims>() : scr_doubles<Hg_dims>();
+}
 template <class M> static size_t rcs_doubles() { return (size_t)NC * (Lay<M>::NA_IT + Lay<M>::NB_IT) * NT; }
 size_t smem_rcs_doubles_per_block(int mech_id)
 {

@@ -6,7 +6,7 @@
 #include "ros_common.cuh"
 
 #ifndef SMEM_NC
-#define SMEM_NC 3          // cells integrated in lock step by one thread block
+#define SMEM_NC 3          // cells integrated in lock step by one thread block (measured on B200: 2 -> 156k, 3 -> 199k, 4 -> 160k cells/s)
 #endif
 #define SMEM_NW 12         // warps per block
 // With 2 cells per block the tables of the triangular sweeps (used 4x per attempt) stay resident in shared
@@ -15,9 +15,19 @@
 #if SMEM_NC <= 2
 #define SMEM_SWEEP_RESIDENT 1
 #define SMEM_RS 6          // ring slots (512-byte chunk rows) per warp for the streamed tables
-#else
+#elif SMEM_NC == 3
 #define SMEM_SWEEP_RESIDENT 0
 #define SMEM_RS 4
+#else
+// 4 cells: the rate / partial-derivative scratch moves to a per-block global buffer (L2 resident, read with
+// ld.global.cg by the vdot / jvs rounds) and the ring shrinks to 3 slots
+#define SMEM_SWEEP_RESIDENT 0
+#define SMEM_RS 3
+#endif
+#if SMEM_NC >= 4
+#define SMEM_SCR_GLOBAL 1
+#else
+#define SMEM_SCR_GLOBAL 0
 #endif
 
 struct SmemArgs {
@@ -35,6 +45,7 @@ struct SmemArgs {
   const double *coefs;                    // [ncoef] stoichiometric coefficients (signed)
   const double *lit;                      // [nlit] literal pool
   double *rcs;                            // per-block scratch: rate constants in item order, [blocks][NC][items]
+  double *scr;                            // per-block A(r)/B(m) scratch when it is not in shared memory
   // byte offsets of the runtime-sized shared-memory regions
   int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
 };
@@ -50,4 +61,5 @@ struct SmemHostPlan {
 bool smem_kernel_supports(int mech_id);
 int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, SmemHostPlan &hp);
 size_t smem_rcs_doubles_per_block(int mech_id);
+size_t smem_scr_doubles_per_block(int mech_id);
 cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s);

@@ -62,7 +62,7 @@ def test_smem_kernel_plan_fits_b200(lib):
     from geos_chem_b200 import kpp
     for mech in ("fullchem", "Hg"):
         p = kpp.plan_info(mech)
-        assert 0 < p["smem_bytes"] + 1024 <= 227 * 1024, p
+        assert 0 < p["smem_bytes"] + 16 <= 227 * 1024, p      # + the 16 bytes of static shared memory
         assert p["cells_per_block"] >= 1
     p = kpp.plan_info("fullchem")
     # head/tail split of the elimination DAG: 21 LU rounds and 19 sweep rounds instead of 72 + 68 levels
