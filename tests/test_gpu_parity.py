@@ -175,3 +175,23 @@ def test_hg_mechanism_vs_oracle(lib, oracle):
         assert rel.max() <= 1e-4
         assert same.all() if kernel == "table" else (~same).sum() <= 2
     s.close()
+
+
+def test_standalone_box_model_cli(tmp_path, fx, capsys):
+    """config 1 through the box-model driver (kpp_standalone.F90:97-169): the sample file is re-emitted from the
+    committed fixture, integrated on the GPU, and must pass the driver's own two consistency checks."""
+    from geos_chem_b200 import sample, standalone
+    s = {k: fx[k] for k in ("level", "cosSZA", "Hstart", "Hexit", "fileTotSteps", "OperatorTimestep", "pressure_hPa",
+                            "temperature_K", "numden", "h2o_vmr", "cloud_fraction", "longitude", "latitude",
+                            "location", "timestamp", "ICNTRL", "RCNTRL", "names")}
+    s["C"], s["ATOL"], s["R"], s["A"] = list(fx["C"]), list(fx["ATOL"]), list(fx["R"]), list(fx["A"])
+    p = tmp_path / "Beijing_L1_20190701_0040.txt"
+    p.write_text(sample.format_sample(s))
+    out = tmp_path / "out.txt"
+    for kernel in (1, 0):
+        rc = standalone.main([str(p), str(out), "--kernel", str(kernel)])
+        txt = capsys.readouterr().out
+        assert rc == 0, txt
+        assert "( standalone):    12" in txt and "Warning" not in txt
+        lines = out.read_text().splitlines()
+        assert lines[0].startswith("Species Name,") and len(lines) == 1 + 356
