@@ -424,7 +424,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
   A.resident = h->sm_res.as<uint4>(); A.res_rows = (int)(p.resident.size() / 128);
   A.boff = h->sm_boff.as<uint16_t>(); A.nresb = (int)p.boff.size();
   A.dir = h->sm_dir.as<uint32_t>(); A.ndir = (int)p.dir.size();
-  A.o_lu = p.o_lu; A.n_lu = p.n_lu; A.o_fwd = p.o_fwd; A.n_fwd = p.n_fwd; A.o_bwd = p.o_bwd; A.n_bwd = p.n_bwd;
+  A.o_lu = p.o_lu; A.n_lu = p.n_lu; A.o_fwd = p.o_fwd; A.n_fwd = p.n_fwd; A.o_bwd = p.o_bwd; A.n_bwd = p.n_bwd; A.o_fwd1 = p.o_fwd1;
   A.tpos = h->sm_tpos.as<uint16_t>();
   A.diag = h->sm_diag.as<uint16_t>(); A.crow = h->sm_crow.as<uint16_t>();
   A.aw = h->sm_aw.as<uint32_t>(); A.bw = h->sm_bw.as<uint32_t>();

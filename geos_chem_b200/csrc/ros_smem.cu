@@ -578,12 +578,8 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           round_barrier((d >> 16) & 15, warp);
         }
         PROF(3);
-        if (warp < NC) tail_lu<M>(G + warp * L::GS, tposT, lane);
-        __syncthreads();
-        PROF(4);
-        // row i: singular test (:1985), reciprocal diagonal, U row scaled by it
-        if (tid < N) {
-          const int dp = diag[tid], e = crow[tid + 1];
+        auto post_lu_row = [&](int i) {     // singular test (:1985), reciprocal diagonal, U row scaled by it
+          const int dp = diag[i], e = crow[i + 1];
 #pragma unroll
           for (int c = 0; c < NC; c++) {
             const double d = G[c * L::GS + dp];
@@ -592,7 +588,38 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
             G[c * L::GS + dp] = rdv;
             for (int p = dp + 1; p < e; p++) G[c * L::GS + p] *= rdv;
           }
+        };
+#if SMEM_OVERLAP
+        // Warps 0..NC-1 factorise the tail block; meanwhile the other warps scale the head rows and run
+        // the forward head rounds of stage 1 (right-hand side Fcn0): those only read L entries of head
+        // columns, which are final, and never touch the tail block.
+        if (tid < N) {
+#pragma unroll
+          for (int c = 0; c < NC; c++) X[c * N + tid] = F0[c];
         }
+        __syncthreads();
+        if (warp < NC) {
+          tail_lu<M>(G + warp * L::GS, tposT, lane);
+        } else {
+          for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) post_lu_row(i);
+#pragma unroll 1
+          for (int r = 0; r < P.n_fwd; r++) {
+            const unsigned d = dir[P.o_fwd1 + r];
+            const int nb = d & 0xfff, W = (d >> 12) & 15, wv = warp - NC;
+            if (wv < W)
+              for (int b = wv; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR);
+            asm volatile("bar.sync 12, %0;" :: "n"((NW - NC) * 32) : "memory");
+          }
+        }
+        __syncthreads();
+        PROF(4);
+        if (tid >= M::HEAD && tid < N) post_lu_row(tid);
+#else
+        if (warp < NC) tail_lu<M>(G + warp * L::GS, tposT, lane);
+        __syncthreads();
+        PROF(4);
+        if (tid < N) post_lu_row(tid);
+#endif
         PROF(5);
       }
       // ---- the stages that use this evaluation: ip 0 -> stages 1 and 2, ip 1 -> stage 3, ip 2 -> stage 4
@@ -600,7 +627,8 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 #pragma unroll 1
       for (int q = 0; q < nsolve; q++) {
         const int st = (ip == 0) ? q : ip + 1;
-        if (tid < N) {          // right-hand side K_st = Fcn + sum_j C(st,j)/H K_j
+        const bool fwd_done = SMEM_OVERLAP && st == 0;       // stage 1: forward head rounds already ran beside tail_lu
+        if (tid < N && !fwd_done) {          // right-hand side K_st = Fcn + sum_j C(st,j)/H K_j
 #pragma unroll
           for (int c = 0; c < NC; c++) {
             double v;
@@ -667,7 +695,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         }
 #else
 #pragma unroll 1
-        for (int r = 0;; r++) {
+        for (int r = fwd_done ? P.n_fwd : 0;; r++) {
           if (r == P.n_fwd) tails();
           if (r == n_tot) break;
           const unsigned d = dir[P.o_fwd + r];
@@ -837,6 +865,10 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   for (int r = r0(4); r < r1(4); r++) dr.push_back(r);
   hp.o_bwd = (int)dr.size(); hp.n_bwd = r1(5) - r0(5);
   for (int r = r0(5); r < r1(5); r++) dr.push_back(r);
+  // second copy of the forward rounds, scheduled on warps NC..NW-1 (they run beside the tail factorisation)
+  hp.o_fwd1 = (int)dr.size();
+  const int n_shift = SMEM_OVERLAP ? hp.n_fwd : 0;
+  for (int r = r0(4); r < r0(4) + n_shift; r++) dr.push_back(r);
   // resident bundles: all bundles of the fwd and bwd rounds, in directory order
   hp.resident.clear(); hp.boff.clear();
   std::vector<int> bfirst(dr.size(), 0);
@@ -855,7 +887,12 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   for (size_t i = 0; i < dr.size(); i++) {
     int r = dr[i], nb = nbundles(r), W = nwarps(r);
     if (nb >= 4096) return -4;
-    bool last = (i + 1 == dr.size()) || (int)i + 1 == hp.o_lu || (int)i + 1 == hp.o_fwd || (int)i + 1 == hp.o_bwd || i < 2;
+    if ((int)i >= hp.o_fwd1) {            // warp-shifted rounds: at most NW-NC warps, their own barrier
+      int Ws = nb < NW - NC ? nb : NW - NC;
+      hp.dir[i] = (uint32_t)nb | ((uint32_t)Ws << 12);
+      continue;
+    }
+    bool last = ((int)i + 1 == hp.o_fwd1) || (int)i + 1 == hp.o_lu || (int)i + 1 == hp.o_fwd || (int)i + 1 == hp.o_bwd || i < 2;
     int Wn = last ? NW : nwarps(dr[i + 1]);
     int Pb = last ? NW : (W > Wn ? W : Wn);
     uint32_t div = (S->rounds[3 * r + 2] & 0x10) ? 1u : 0u;
@@ -863,23 +900,25 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   }
   // per-warp streams in the order one Rodas3 attempt consumes them: vdot, jvs, lu rounds, [sweeps x2], vdot,
   // [sweeps], vdot, [sweeps]  (the sweeps only when their tables are not resident)
-  std::vector<int> order;
-  auto push_sweeps = [&]() {
+  std::vector<std::pair<int, int>> order;        // (round, first warp)
+  auto push_sweeps = [&](bool shifted_fwd) {
     if (SMEM_SWEEP_RESIDENT) return;
-    for (int r = r0(4); r < r1(4); r++) order.push_back(r);
-    for (int r = r0(5); r < r1(5); r++) order.push_back(r);
+    for (int r = r0(4); r < r1(4); r++) order.push_back({r, shifted_fwd ? NC : 0});
+    for (int r = r0(5); r < r1(5); r++) order.push_back({r, 0});
   };
-  order.push_back(r0(0)); order.push_back(r0(1));
-  for (int r = r0(2); r < r1(2); r++) order.push_back(r);
-  push_sweeps(); push_sweeps();
-  order.push_back(r0(0)); push_sweeps();
-  order.push_back(r0(0)); push_sweeps();
+  order.push_back({r0(0), 0}); order.push_back({r0(1), 0});
+  for (int r = r0(2); r < r1(2); r++) order.push_back({r, 0});
+  push_sweeps(SMEM_OVERLAP); push_sweeps(false);
+  order.push_back({r0(0), 0}); push_sweeps(false);
+  order.push_back({r0(0), 0}); push_sweeps(false);
   std::vector<std::vector<uint32_t>> ws(NW);
-  for (int r : order) {
+  for (auto &rw : order) {
+    int r = rw.first, w0 = rw.second;
     int W = nwarps(r);
+    if (w0 > 0 && W > NW - w0) W = NW - w0;
     uint32_t b0 = S->rounds[3 * r], b1 = S->rounds[3 * r + 1];
     for (uint32_t b = b0; b < b1; b++) {
-      int w = (int)((b - b0) % (uint32_t)W);
+      int w = w0 + (int)((b - b0) % (uint32_t)W);
       for (uint32_t row = S->brow[b]; row < S->brow[b + 1]; row++)
         ws[w].insert(ws[w].end(), S->chunks + (size_t)row * 128, S->chunks + (size_t)(row + 1) * 128);
     }

@@ -24,6 +24,11 @@
 #define SMEM_SWEEP_RESIDENT 0
 #define SMEM_RS 3
 #endif
+// Run stage 1's forward head rounds and the scaling of the head rows on warps NC..NW-1 while warps 0..NC-1
+// factorise the tail block (needs the streamed sweep tables: the schedule of those rounds is warp-shifted).
+#ifndef SMEM_OVERLAP
+#define SMEM_OVERLAP (!SMEM_SWEEP_RESIDENT)
+#endif
 #if SMEM_NC >= 4
 #define SMEM_SCR_GLOBAL 1
 #else
@@ -38,7 +43,7 @@ struct SmemArgs {
   const uint4 *resident; int res_rows;
   const uint16_t *boff; int nresb;        // first chunk row of every resident bundle
   const uint32_t *dir; int ndir;          // round directory: nb | W<<12 | P<<16 | div<<20 | first resident bundle<<21
-  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd;
+  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   const uint16_t *tpos;                   // [32][32]
   const uint16_t *diag, *crow;            // [nvar], [nvar+1]
   const uint32_t *aw, *bw;                // [nreact][2], [nb][2] encoded rate / partial-derivative terms
@@ -54,7 +59,7 @@ struct SmemHostPlan {
   int warp_off[SMEM_NW], warp_rows[SMEM_NW];
   std::vector<uint32_t> stream, resident, dir, aw, bw;
   std::vector<uint16_t> boff, diag, crow;
-  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd;
+  int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
 };
 
