@@ -249,10 +249,12 @@ __device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int l
     const unsigned p = tposT[k * 32 + lane];
     r[k] = (p != TNONE) ? Gc[p] : 0.0;
   }
+  // The reciprocal of the next pivot is started as soon as its column has been updated (first batch),
+  // so its latency overlaps the rest of the row update.
+  double rinv = 1.0 / __shfl_sync(FULLMASK, r[0], 0);
 #pragma unroll 1
   for (int j = 0; j < m; j++) {
-    const double dj = __shfl_sync(FULLMASK, r[0], j);
-    const double l = (lane > j) ? r[0] / dj : 0.0;
+    const double l = (lane > j) ? r[0] * rinv : 0.0;
     const unsigned p = tposT[j * 32 + lane];
     if (p != TNONE) Gc[p] = (lane > j) ? l : r[0];         // column j is final: L multiplier, diagonal or U entry
     // update column j+k and rotate it to slot k-1; shuffles issued in batches so their latency overlaps
@@ -268,6 +270,7 @@ __device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int l
 #pragma unroll
       for (int q = 0; q < 8; q++)
         if (k0 + q < m) r[k0 + q - 1] = fma(-l, __hiloint2double(hi[q], lo[q]), r[k0 + q]);
+      if (k0 == 1) rinv = 1.0 / __shfl_sync(FULLMASK, r[0], (j + 1) & 31);
     }
     r[m - 1] = 0.0;
   }
