@@ -20,12 +20,12 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 
 # translation unit -> extra flags
 UNITS = {
-    "gckpp_gpu.cu": [],
     "kernels_misc.cu": [],
     # arithmetic-reference kernel: no FMA contraction so sums round like the reference's
     "ros_generic.cu": ["-fmad=false"],
     # production kernel: shared-memory-resident, FMA allowed
-    "ros_smem.cu": (["-DSMEM_PROFILE"] if os.environ.get("GCKPP_SMEM_PROFILE") else []),
+    "ros_smem.cu": (["-DSMEM_PROFILE"] if os.environ.get("GCKPP_SMEM_PROFILE") else []) + os.environ.get("GCKPP_SMEM_DEFS", "").split(),
+    "gckpp_gpu.cu": os.environ.get("GCKPP_SMEM_DEFS", "").split(),
 }
 
 

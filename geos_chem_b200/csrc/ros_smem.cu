@@ -349,7 +349,6 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   uint32_t *dir = reinterpret_cast<uint32_t *>(smem + P.s_dir);
   uint16_t *diag = reinterpret_cast<uint16_t *>(smem + P.s_diag);
   uint16_t *crow = reinterpret_cast<uint16_t *>(smem + P.s_crow);
-  __shared__ int s_exhausted;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const RosOpts &o = a.o;
@@ -371,7 +370,6 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
     s.have = 0; s.cell = -1; s.H = 1.0; s.T = 0.0; s.ghinv = 2.0; s.newstep = 0; s.skip = 1; s.sing = 0;
     s.out_cell = -1; s.in_cell = -1; s.ierr = 0; s.accept = 0;
   }
-  if (tid == 0) s_exhausted = 0;
 
   // The rate phases are thread-private: thread t evaluates reactions t, t+NT, ... (and the partial
   // derivatives t, t+NT, ... of the Jacobian).  Their rate constants are kept in ITEM order in a
@@ -391,6 +389,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
     rtol_i = o.VectorTol ? a.rtol[tid] : a.rtol[0];
   }
   unsigned long long acc_stp = 0, acc_acc = 0, acc_fail = 0, acc_done = 0;   // meaningful in threads < NC
+  bool exhausted = false;      // control threads: the work counter ran past nwork
 
   Reader rd;
   rd.gsrc = P.stream + (size_t)P.warp_off[warp] * 32 + lane;
@@ -428,10 +427,10 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         if (s.ierr < 0) acc_fail++;
         s.have = 0; s.ierr = 0; s.cell = -1; s.H = 1.0; s.T = 0.0;
       }
-      if (!s.have && !s_exhausted) {
+      if (!s.have && !exhausted) {
         int w = atomicAdd(a.next, 1);
         if (w >= a.nwork) {
-          s_exhausted = 1;      // benign race: every writer stores 1
+          exhausted = true;
         } else {
           int cell = a.cell_list ? a.cell_list[w] : w;
           s.cell = cell; s.in_cell = cell;

@@ -17,7 +17,9 @@
 #define SMEM_RS 6          // ring slots (512-byte chunk rows) per warp for the streamed tables
 #elif SMEM_NC == 3
 #define SMEM_SWEEP_RESIDENT 0
+#ifndef SMEM_RS
 #define SMEM_RS 4
+#endif
 #else
 // 4 cells: the rate / partial-derivative scratch moves to a per-block global buffer (L2 resident, read with
 // ld.global.cg by the vdot / jvs rounds) and the ring shrinks to 3 slots
