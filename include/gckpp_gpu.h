@@ -52,7 +52,7 @@ int gckpp_gpu_dims(int mech_id, int32_t *dims);
 const char *gckpp_gpu_spc_name(int mech_id, int i);
 
 /* Create a solver instance on CUDA device `device`, sized for up to max_cells per call
- * (larger calls are processed in waves).  Replaces nothing in the reference (KPP has no
+ * (a sizing hint: buffers grow on demand).  Replaces nothing in the reference (KPP has no
  * state beyond its module variables); owns device buffers and a stream. */
 int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_handle_t **handle);
 int gckpp_gpu_finalize(gckpp_gpu_handle_t *handle);
