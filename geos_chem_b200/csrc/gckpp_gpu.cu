@@ -100,6 +100,7 @@ struct gckpp_gpu_handle {
   SmemArgs sargs{};
   DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
+  DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   double stats[16]{};
 };
 
@@ -149,6 +150,9 @@ static WsLayout make_layout(const gckpp_host_tables_t *T)
   L.RC = o; o += T->nreact;
   L.AB = o; o += (T->nreact > T->nb ? T->nreact : T->nb);
   L.W = o;  o += T->nvar;
+  L.PR = o; o += T->nvar;              // auto-reduce: initial Prod, Loss and the keep mask
+  L.LS = o; o += T->nvar;
+  L.MK = o; o += T->nvar;
   L.total = o;
   return L;
 }
@@ -207,7 +211,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
-                    &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->keep_spc, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -443,6 +447,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
 // The shared-memory kernel implements the method GEOS-Chem selects (Rodas3, ICNTRL(3) = 0 or 4).
 static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
+  if (d.autoreduce) return false;            // auto-reduce runs on the table-driven kernel
   if (h->opt_kernel == 0) return false;      // "kernel"=0 forces the table-driven, reference-order kernel
   if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->mech_id)) return false;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
@@ -468,6 +473,10 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   a.work = h->work.as<double>(); a.ws_stride = (size_t)h->L.total * 32;
   a.next = h->next.as<int>(); a.sums = h->sums.as<unsigned long long>();
   a.L = h->L; a.o = d.o;
+  // auto-reduce options as Rosenbrock() decodes them (gckpp_Integrator.F90:390-394, :479-486)
+  a.ar_on = d.autoreduce; a.ar_target = d.ICNTRL[13]; a.ar_keep_active = h->keep_n > 0;
+  a.ar_threshold = d.RCNTRL[11] > 0.0 ? d.RCNTRL[11] : 1.0e2; a.ar_ratio = d.RCNTRL[13];
+  a.ar_keep_spc = h->keep_n > 0 ? h->keep_spc.as<unsigned char>() : nullptr;
   CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
   if (h->T->nnz == 0) {   // carbon: forward Euler
     CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
@@ -506,7 +515,8 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return rc;
   }
-  if (d.autoreduce) return fail(-12, "auto-reduce (ICNTRL(12)=1) is not available in this build");
+  if (d.autoreduce && d.ICNTRL[12] == 1) return fail(-12, "the append variant of auto-reduce (ICNTRL(13)=1) is not available in this build");
+  if (d.autoreduce && !T->fun_split) return fail(-12, "auto-reduce needs the split ODE function (fullchem)");
   for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
   if (atol && rtol) {
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
@@ -762,6 +772,21 @@ extern "C" int gckpp_gpu_solve(gckpp_gpu_handle_t *h, int ncell, const double *j
   CUDA_TRY(launch_solve_cells(h->M, ncell, J, X, h->stream));
   CUDA_TRY(cudaMemcpyAsync(x, X, sizeof(double) * T->nvar * nc, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_set_keep_active(gckpp_gpu_handle_t *h, int n, const int32_t *idx0)
+{
+  if (!h || n < 0 || (n > 0 && !idx0)) return fail(-10, "gckpp_gpu_set_keep_active: bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<unsigned char> m((size_t)h->T->nvar, 0);
+  for (int i = 0; i < n; i++) {
+    if (idx0[i] < 0 || idx0[i] >= h->T->nvar) return fail(-10, "gckpp_gpu_set_keep_active: index %d out of range", idx0[i]);
+    m[idx0[i]] = 1;
+  }
+  if (h->keep_spc.ensure(m.size())) return fail(-1002, "out of device memory");
+  CUDA_TRY(cudaMemcpy(h->keep_spc.p, m.data(), m.size(), cudaMemcpyHostToDevice));
+  h->keep_n = n;
   return 0;
 }
 

@@ -30,7 +30,7 @@ struct RosOpts {
 };
 
 struct WsLayout {              // offsets in doubles per lane
-  int Y, YN, F0, FC, K, G, RC, AB, W, total;
+  int Y, YN, F0, FC, K, G, RC, AB, W, PR, LS, MK, total;    // PR/LS/MK: auto-reduce Prod, Loss, keep mask
 };
 
 struct RosArgs {
@@ -48,6 +48,10 @@ struct RosArgs {
   unsigned long long *sums;    // [0] sum Nstp [1] sum Nacc [2] cells with ierr<0 [3] cells done
   WsLayout L;
   RosOpts o;
+  // auto-reduce (ros_yIntegrator, gckpp_Integrator.F90:789-1237): ICNTRL(12), RCNTRL(12), ICNTRL(14), RCNTRL(14)
+  int ar_on, ar_target, ar_keep_active;
+  double ar_threshold, ar_ratio;
+  const unsigned char *ar_keep_spc;        // [nvar] keepSpcActive, or NULL
 };
 
 enum { Nfun = 0, Njac, Nstp, Nacc, Nrej, Ndec, Nsol, Nsng };

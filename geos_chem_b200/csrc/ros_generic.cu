@@ -35,7 +35,9 @@ __device__ void g_rates(const MechDev &M, const double *yv, const double *rc, do
 }
 
 // Vdot = Fun(Y): split form (P - D*V) for fullchem, aggregate for Hg/carbon (see FunTemplate).
-__device__ void g_fun(const MechDev &M, const double *yv, const double *rc, double *A, double *out, size_t st)
+// pd != nullptr && wr: also store Prod = P_VAR and Loss = D_VAR (FunSplitF, gckpp_Integrator.F90:2518-2547)
+__device__ void g_fun(const MechDev &M, const double *yv, const double *rc, double *A, double *out, size_t st,
+                      double *prod = nullptr, double *loss = nullptr, bool wr = false)
 {
   g_rates(M, yv, rc, A, st);
   if (M.fun_split) {
@@ -46,6 +48,7 @@ __device__ void g_fun(const MechDev &M, const double *yv, const double *rc, doub
       e = __ldg(M.d_ptr + i + 1);
       for (int k = __ldg(M.d_ptr + i); k < e; k++) D = D + term_eval(__ldg(M.d_term + k), yv, rc, M.lit, st);
       out[(size_t)i * st] = P - D * yv[(size_t)i * st];
+      if (prod && wr) { prod[(size_t)i * st] = P; loss[(size_t)i * st] = D; }
     }
   } else {
     for (int i = 0; i < M.nvar; i++) {
@@ -129,11 +132,13 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
   double *Y = ws + (size_t)L.Y * st, *YN = ws + (size_t)L.YN * st, *F0 = ws + (size_t)L.F0 * st;
   double *FC = ws + (size_t)L.FC * st, *K = ws + (size_t)L.K * st, *G = ws + (size_t)L.G * st;
   double *RC = ws + (size_t)L.RC * st, *AB = ws + (size_t)L.AB * st, *W = ws + (size_t)L.W * st;
+  double *PR = ws + (size_t)L.PR * st, *LS = ws + (size_t)L.LS * st, *MK = ws + (size_t)L.MK * st;   // auto-reduce only
   const double Dir = (double)o.Direction;
 
   // per-lane integration state
   bool have = false, exhausted = false, newstep = false;
-  bool RejectLastH = false, RejectMoreH = false;
+  bool RejectLastH = false, RejectMoreH = false, reduced = false;
+  double arthr = 0.0;
   int cell = -1, nconsec = 0, ierr_cell = 0;
   int ist[8];
   double T = 0.0, H = 0.0, Hexit = 0.0, Hnew_out = 0.0, Texit = 0.0;
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
           H = fmin(fmax(fabs(o.Hmin), fabs(Hstart)), fabs(o.Hmax));      // :637
           if (fabs(H) <= 10.0 * o.Roundoff) H = 1.0E-5;
           H = Dir * H;
-          RejectLastH = false; RejectMoreH = false;
+          RejectLastH = false; RejectMoreH = false; reduced = false; arthr = 0.0;
           have = true; newstep = true; nconsec = 0; ierr_cell = 0;
         }
       }
@@ -178,6 +183,18 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
       }
       if (have && ierr_cell != 0) {
         // ---- finalize this cell
+        if (a.ar_on && ierr_cell == 1 && reduced) {
+          // 1st order solution for the removed species (AutoReduce_1stOrder, :1702-1712), initial Prod/Loss
+          for (int i = 0; i < N; i++) {
+            if (MK[(size_t)i * st] == 0.0) {
+              const double P = PR[(size_t)i * st], k = LS[(size_t)i * st], y = Y[(size_t)i * st];
+              if (k > 1.e-30 && y > 1.e-30) {
+                const double term = P / k;
+                Y[(size_t)i * st] = term + (y - term) * exp(-k * (o.Tend - o.Tstart));
+              }
+            }
+          }
+        }
         for (int s = 0; s < M.nspec; s++) a.conc_out[(size_t)s * a.ncell + cell] = Y[(size_t)s * st];
         if (a.istatus)
 #pragma unroll
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
           a.rstatus[cell] = Texit;
           a.rstatus[(size_t)a.ncell + cell] = Hexit;
           a.rstatus[(size_t)2 * a.ncell + cell] = Hnew_out;
-          a.rstatus[(size_t)3 * a.ncell + cell] = 0.0;
+          a.rstatus[(size_t)3 * a.ncell + cell] = arthr;
         }
         if (a.ierr) a.ierr[cell] = ierr_cell;
         acc_stp += ist[Nstp]; acc_acc += ist[Nacc]; acc_done++;
@@ -200,7 +217,23 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
     // ---- one Rosenbrock attempt for every lane of the warp ---------------------------------
     // Fcn0 = Fun(Y) at the start of a step (:668); lanes repeating a rejected step recompute
     // the identical values, so no predicate is needed on the data.
-    if (__any_sync(FULLMASK, have && newstep)) g_fun(M, Y, RC, AB, F0, st);
+    if (__any_sync(FULLMASK, have && newstep))
+      g_fun(M, Y, RC, AB, F0, st, a.ar_on ? PR : nullptr, LS, have && newstep && !reduced && T == o.Tstart);
+    if (a.ar_on && have && newstep && !reduced) {
+      // species whose production and loss are both below the threshold leave the implicit system (:918-962)
+      double thr = a.ar_threshold;
+      if (a.ar_target > 0) {
+        const size_t t = (size_t)(a.ar_target - 1) * st;
+        thr = a.ar_ratio * fmax(LS[t] * Y[t], PR[t]);
+        arthr = thr;
+      }
+      for (int i = 0; i < N; i++) {
+        const bool keep = a.ar_keep_active && a.ar_keep_spc && a.ar_keep_spc[i];
+        const bool rmv = !keep && fabs(LS[(size_t)i * st] * Y[(size_t)i * st]) < thr && fabs(PR[(size_t)i * st]) < thr;
+        MK[(size_t)i * st] = rmv ? 0.0 : 1.0;
+      }
+      reduced = true;
+    }
     if (have && newstep) {
       ist[Nfun]++;
       if (!o.Autonomous) ist[Nfun]++;   // ros_FunTimeDerivative: with ICNTRL(15)=-1 Fun does not depend on T, dFdT == 0
@@ -211,6 +244,17 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
     // same values, and 45 KB less state per cell.
     double ghinv = 1.0 / (Dir * H * o.Gamma[0]);
     g_jac(M, Y, RC, AB, G, -1.0, ghinv, st);
+    if (a.ar_on && have && reduced) {
+      // the compressed system of ros_cPrepareMatrix, expressed on the full pattern: rows and columns of the
+      // removed species become identity rows/columns; kept rows then see exactly the reference's operations
+      for (int i = 0; i < N; i++) {
+        const bool ki = MK[(size_t)i * st] != 0.0;
+        const int c1 = __ldg(M.crow + i + 1);
+        for (int k = __ldg(M.crow + i); k < c1; k++)
+          if (!ki || MK[(size_t)__ldg(M.icol + k) * st] == 0.0) G[(size_t)k * st] = 0.0;
+        if (!ki) G[(size_t)__ldg(M.diag + i) * st] = 1.0;
+      }
+    }
     int ising = g_decomp(M, G, W, st);
     bool skip = false;
     if (have) {
@@ -248,6 +292,7 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
           double HC = o.C[(is - 1) * (is - 2) / 2 + j - 1] / (Dir * H);
           if (HC != 0.0) v = v + HC * K[((size_t)N * (j - 1) + i) * st];
         }
+        if (a.ar_on && have && reduced && MK[(size_t)i * st] == 0.0) v = 0.0;     // K of a removed species stays 0
         Ki[(size_t)i * st] = v;
       }
       g_solve(M, G, Ki, st);

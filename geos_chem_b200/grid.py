@@ -174,3 +174,17 @@ def replicate_fixture(n, fx=None):
     rcntrl[2] = fx["Hstart"]
     return dict(conc=conc, rconst=rconst, atol=fx["ATOL"][:nvar].copy(), rtol=np.full(nvar, 0.5e-2),
                 icntrl=icntrl, rcntrl=rcntrl, hstart=np.full(n, fx["Hstart"]), dt=fx["OperatorTimestep"])
+
+
+# species the auto-reduce solver never removes (fullchem_AutoReduce_KeepHalogensActive,
+# KPP/fullchem/fullchem_AutoReduceFuncs.F90:69-108; Shen et al. 2020 GMD Table 1)
+KEEP_ACTIVE_HALOGENS = ["AERI", "Br", "Br2", "BrCl", "BrNO2", "BrNO3", "BrO", "BrSALA", "BrSALC", "HBr", "HOBr", "Cl",
+                        "Cl2", "Cl2O2", "ClNO2", "ClNO3", "ClO", "ClOO", "OClO", "HCl", "HOCl", "I", "I2", "IO", "I2O2",
+                        "HI", "ISALA", "ISALC", "I2O4", "I2O3", "INO", "IONO", "IONO2", "ICl", "IBr", "HOI", "SALACl",
+                        "SALCCl", "SALAAL", "SALCAL"]
+
+
+def keep_active_indices(names):
+    """0-based indices of KEEP_ACTIVE_HALOGENS in SPC_NAMES (Fortran identifiers are case-insensitive)"""
+    up = {n.upper(): i for i, n in enumerate(names)}
+    return [up[k.upper()] for k in KEEP_ACTIVE_HALOGENS]

@@ -65,6 +65,7 @@ def load_library(path=None):
     L.gckpp_gpu_fp64_peak.argtypes = [C.c_int, dp, dp]
     L.gckpp_gpu_last_error.restype = C.c_char_p
     L.gckpp_gpu_plan_info.argtypes = [C.c_int, ip]
+    L.gckpp_gpu_set_keep_active.argtypes = [vp, C.c_int, ip]
     _lib = L
     return L
 
@@ -73,7 +74,7 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
            "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
            "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error", "gckpp_gpu_set_stream",
-           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info"]
+           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active"]
 
 
 def plan_info(mech):
@@ -146,6 +147,14 @@ class KppSolver:
 
     def set_option(self, key, value):
         rc = self.L.gckpp_gpu_set_option(self.h, key.encode(), int(value))
+        if rc != 0:
+            raise KppError(self.L.gckpp_gpu_last_error().decode())
+
+    def set_keep_active(self, idx0):
+        """keepSpcActive of the auto-reduce solver: 0-based variable-species indices that are never removed
+        (fullchem_AutoReduceFuncs.F90:40-140); an empty list switches keepActive off"""
+        a = np.ascontiguousarray(idx0, np.int32)
+        rc = self.L.gckpp_gpu_set_keep_active(self.h, int(a.size), a.ctypes.data_as(C.POINTER(C.c_int32)))
         if rc != 0:
             raise KppError(self.L.gckpp_gpu_last_error().decode())
 

@@ -146,6 +146,15 @@ int gckpp_gpu_fp64_peak(int device, double *tflops_out, double *ms_out);
  * stats[9] device time of the whole call (rate constants + integration + retry) [ms]. */
 int gckpp_gpu_last_stats(gckpp_gpu_handle_t *handle, double *stats /* [16] */);
 
+/* keepActive / keepSpcActive of the auto-reduce solver (gckpp_Global; set by fullchem_AutoReduce_SetKeepActive
+ * and fullchem_AutoReduce_KeepHalogensActive, fullchem_AutoReduceFuncs.F90:40-140): n 0-based variable-species
+ * indices that are never removed from the implicit system; n = 0 switches keepActive off.
+ * Auto-reduce itself is selected like in the reference: ICNTRL(12)=1, threshold RCNTRL(12) (default 100) or,
+ * with a target species ICNTRL(14) > 0, RCNTRL(14) * max(LossY, Prod) of that species; it runs on the
+ * table-driven kernel (ros_yIntegrator, gckpp_Integrator.F90:789-1237); rstatus[3] returns the threshold.
+ * The append variant (ICNTRL(13)=1) is not available (-12). */
+int gckpp_gpu_set_keep_active(gckpp_gpu_handle_t *handle, int n, const int32_t *idx0);
+
 /* Host-only description of the shared-memory kernel's static plan for a mechanism (no GPU needed):
  * info[0] dynamic shared memory per block [bytes], info[1] streamed table rows (512 B) per attempt,
  * info[2] resident table rows, info[3] rounds in the directory, info[4..6] LU / forward / backward

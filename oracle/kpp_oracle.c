@@ -404,11 +404,7 @@ static int feuler_integrator(ros_ctx_t *c, double *Y, double Tstart, double Tend
   return ierr;
 }
 
-int kpp_oracle_ar_integrate(ros_ctx_t *c, const ros_method_t *ros, double *Y, double Tstart, double Tend,
-                            double *Tout, const double *AbsTol, const double *RelTol, int Autonomous,
-                            int VectorTol, int Max_no_steps, double Roundoff, double Hmin, double Hmax,
-                            double Hstart, double FacMin, double FacMax, double FacRej, double FacSafe,
-                            double threshold, int target_spc, double thr_ratio, int append);
+#include "kpp_oracle_ar.c"   /* auto-reduce integrator: needs the static types and helpers above */
 
 /* Integrate + Rosenbrock (:80-162, :165-531) */
 int kpp_oracle_integrate_cell(int mech_id, double tin, double tout, double *C, const double *RCONST,

@@ -64,6 +64,10 @@ int kpp_oracle_update_rconst(int mech_id, int ncell, const double *temp, const d
                              const double *h2o, const double *photol, const double *khet,
                              double *rconst, int nthreads);
 
+/* keepActive / keepSpcActive of the auto-reduce solver (fullchem_AutoReduceFuncs.F90:40-140): 0-based species
+ * indices that are never removed; n = 0 switches keepActive off.  Global (like the Fortran module variable). */
+int kpp_oracle_set_keep_active(int mech_id, int n, const int *idx0);
+
 /* single-cell pieces for unit tests */
 int kpp_oracle_fun(int mech_id, const double *C, const double *RCONST, double *Vdot, double *A);
 int kpp_oracle_jac(int mech_id, const double *C, const double *RCONST, double *JVS);

@@ -39,6 +39,17 @@ class Oracle:
         L.kpp_oracle_jac.argtypes = [C.c_int, _dp, _dp, _dp]
         L.kpp_oracle_decomp.argtypes = [C.c_int, _dp]
         L.kpp_oracle_solve.argtypes = [C.c_int, _dp, _dp]
+        L.kpp_oracle_set_keep_active.argtypes = [C.c_int, C.c_int, _ip]
+
+    def set_keep_active(self, mech, idx0):
+        """keepSpcActive of the auto-reduce solver (global, like the Fortran module variable); [] switches it off"""
+        a = np.ascontiguousarray(idx0, np.int32)
+        if a.size == 0:
+            a = np.zeros(1, np.int32)
+            n = 0
+        else:
+            n = a.size
+        assert self.lib.kpp_oracle_set_keep_active(MECH_ID[mech], n, a) == 0
 
     def dims(self, mech="fullchem"):
         d = np.zeros(7, np.int32)

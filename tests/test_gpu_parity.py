@@ -195,3 +195,46 @@ def test_standalone_box_model_cli(tmp_path, fx, capsys):
         assert "( standalone):    12" in txt and "Warning" not in txt
         lines = out.read_text().splitlines()
         assert lines[0].startswith("Species Name,") and len(lines) == 1 + 356
+
+
+@pytest.mark.parametrize("mode", ["target_OH", "fixed_threshold"])
+def test_autoreduce_vs_oracle(solver, oracle, fx, mode):
+    """config 5: fullchem with the auto-reduce solver (ros_yIntegrator, gckpp_Integrator.F90:789-1237), options as
+    fullchem_AutoReduceFuncs.F90:275-342 sets them.  Parity is unpinned by the reference (no fixture): the GPU
+    (table-driven kernel, mask form of the compressed system) is compared with the oracle's restatement."""
+    names = fx["names"]
+    keep = grid.keep_active_indices(names[:353])
+    g = grid.make_grid("4x5", limit=40000)
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.choice(40000, 600, replace=False))
+    conc = np.ascontiguousarray(g["conc"][:, idx]); hs = g["hstart"][idx]
+    rc = oracle.update_rconst("fullchem", g["temp"][idx], g["numden"][idx], g["h2o"][idx],
+                              np.ascontiguousarray(g["photol"][:, idx]), np.ascontiguousarray(g["khet"][:, idx]))
+    icntrl, rcntrl = g["icntrl"].copy(), g["rcntrl"].copy()
+    icntrl[11] = 1
+    if mode == "target_OH":
+        icntrl[13] = [n.upper() for n in names].index("OH") + 1
+        rcntrl[13] = 5e-5
+    else:
+        rcntrl[11] = 1e3
+    oracle.set_keep_active("fullchem", keep)
+    solver.set_keep_active(keep)
+    try:
+        co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, rcntrl, hstart=hs)
+        c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, rcntrl, hstart=hs)
+        # and the unreduced solution, to show that the option does something
+        cf, _, _, _, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs)
+    finally:
+        oracle.set_keep_active("fullchem", [])
+        solver.set_keep_active([])
+    assert np.array_equal(ierr, ierro)
+    same = np.all(ist == isto, axis=0)
+    rel = _parity(c, co)
+    print("auto-reduce %s: cells with different steps %d, max rel err %.3e; species changed vs full solve: %.1f %%; "
+          "ARthr max rel diff %.2e" % (mode, int((~same).sum()), rel.max(), 100.0 * np.mean(c[:353] != cf[:353]),
+                                       np.abs(rst[3] - rsto[3]).max() / max(np.abs(rsto[3]).max(), 1e-300)))
+    assert rel.max() <= 1e-4
+    assert same.all()
+    assert np.mean(c[:353] != cf[:353]) > 0.5
+    if mode == "target_OH":
+        assert np.allclose(rst[3], rsto[3], rtol=1e-12) and (rst[3] > 0).all()

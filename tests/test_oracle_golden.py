@@ -97,3 +97,33 @@ def test_fma_build_agrees(fx):
     r = grid.replicate_fixture(1, fx)
     c, ist, rst, ierr = o.integrate_cell("fullchem", 0.0, r["dt"], fx["C"], fx["R"], r["atol"], r["rtol"], r["icntrl"], r["rcntrl"])
     assert ierr == 1 and ist[2] == 12 and round(rst[1], 4) == 497.8023
+
+
+def test_autoreduce_oracle_runs_and_keeps_halogens(oracle, fx):
+    """auto-reduce restatement (ros_yIntegrator): with the threshold at 0 nothing is removed and the result is the
+    standard integrator's bit for bit; with the reference's OH-target setting most species change, the kept
+    halogens are integrated implicitly, and RSTATUS(NARthr) reports the threshold.  (Unpinned by the reference.)"""
+    from geos_chem_b200 import grid
+    names = fx["names"]
+    r = grid.replicate_fixture(1, fx)
+    c0, ist0, rst0, ierr0 = oracle.integrate_cell("fullchem", 0.0, r["dt"], r["conc"][:, 0], r["rconst"][:, 0], r["atol"],
+                                                  r["rtol"], r["icntrl"], r["rcntrl"])
+    ic, rc = r["icntrl"].copy(), r["rcntrl"].copy()
+    ic[11] = 1
+    ic[13] = 0                           # the sample's own ICNTRL(14) = ind_OH selects the target-species threshold
+    rc[11] = 1e-300                      # nothing is below this threshold
+    c1, ist1, rst1, ierr1 = oracle.integrate_cell("fullchem", 0.0, r["dt"], r["conc"][:, 0], r["rconst"][:, 0], r["atol"],
+                                                  r["rtol"], ic, rc)
+    assert ierr1 == 1 and np.array_equal(ist1[:8], ist0[:8]) and np.array_equal(c1, c0)
+    ic[13] = [n.upper() for n in names].index("OH") + 1
+    rc[11], rc[13] = 0.0, 5e-5
+    oracle.set_keep_active("fullchem", grid.keep_active_indices(names[:353]))
+    try:
+        c2, ist2, rst2, ierr2 = oracle.integrate_cell("fullchem", 0.0, r["dt"], r["conc"][:, 0], r["rconst"][:, 0],
+                                                      r["atol"], r["rtol"], ic, rc)
+    finally:
+        oracle.set_keep_active("fullchem", [])
+    assert ierr2 == 1 and rst2[3] > 0.0 and ist2[2] >= 1
+    assert np.mean(c2[:353] != c0[:353]) > 0.5
+    big = np.abs(c0) > 1e8               # the abundant species barely notice the reduction
+    assert np.max(np.abs(c2 - c0)[big] / np.abs(c0[big])) < 5e-2
