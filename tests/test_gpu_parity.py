@@ -238,3 +238,25 @@ def test_autoreduce_vs_oracle(solver, oracle, fx, mode):
     assert np.mean(c[:353] != cf[:353]) > 0.5
     if mode == "target_OH":
         assert np.allclose(rst[3], rsto[3], rtol=1e-12) and (rst[3] > 0).all()
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 5, 6])
+def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method):
+    """ICNTRL(3) = 1 Ros2, 2 Ros3, 3 Ros4, 5 Rodas4, 6 Rang3 (gckpp_Integrator.F90:2062-2476): the table-driven
+    kernel takes over (the shared-memory kernel is Rodas3 only) and must follow the oracle step for step."""
+    g = grid.make_grid("4x5", limit=30000)
+    rng = np.random.default_rng(method)
+    idx = np.sort(rng.choice(30000, 200, replace=False))
+    conc = np.ascontiguousarray(g["conc"][:, idx]); hs = g["hstart"][idx]
+    rc = oracle.update_rconst("fullchem", g["temp"][idx], g["numden"][idx], g["h2o"][idx],
+                              np.ascontiguousarray(g["photol"][:, idx]), np.ascontiguousarray(g["khet"][:, idx]))
+    icntrl = g["icntrl"].copy()
+    icntrl[2] = method
+    solver.set_option("kernel", 1)       # the default choice; the library itself must fall back
+    co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
+    c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
+    assert np.array_equal(ierr, ierro)
+    rel = _parity(c, co)
+    same = np.all(ist == isto, axis=0)
+    print("method %d: mean Nstp %.1f, cells with different steps %d, max rel err %.3e" % (method, ist[2].mean(), int((~same).sum()), rel.max()))
+    assert rel.max() <= 1e-4 and same.all()
