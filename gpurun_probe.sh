@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "other_rosenbrock" -s 2>&1 | tail -12
+( timeout 300 python tools/smem_debug.py small ) 2>&1 | tail -3
+timeout 200 python tools/variant_bench.py own 2>&1 | tail -1
