@@ -2,7 +2,7 @@
 """Quick GPU-vs-oracle check with statistics (run on the GPU box): parity percentiles, step-count
 histograms side by side, kernel time.  Usage: python tools/gpu_check.py [ncells] [warm|cold]"""
 import os, sys, time
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import numpy as np
 from geos_chem_b200 import grid, kpp
 from oracle.pyoracle import Oracle

@@ -15,5 +15,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ros_
     python bench.py --steps 1 --warmup 0 --cells 47360 --no-cpu-baseline "$@" > $out/ncu_full.log 2>&1
 ncu -i $out/ros_full.ncu-rep --page raw --csv > $out/ros_full_raw.csv 2>/dev/null
 ncu -i $out/ros_full.ncu-rep --page details --csv > $out/ros_full_details.csv 2>/dev/null
-( timeout 600 python tools/gpu_check.py 20000 warm ) > $out/gpu_check.log 2>&1
+( timeout 600 python tests/gpu_tools/gpu_check.py 20000 warm ) > $out/gpu_check.log 2>&1
 tail -3 $out/pytest_gpu.log; tail -2 $out/bench.log; tail -1 $out/bench_ref.log; tail -12 $out/gpu_check.log
