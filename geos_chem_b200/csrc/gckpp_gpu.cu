@@ -101,6 +101,10 @@ struct gckpp_gpu_handle {
   DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
+  // pipelined host entry: copy streams and the identity cell list
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  DevBuf ident; int ident_n = 0;
+  int opt_chunks = 4;
   double stats[16]{};
 };
 
@@ -211,10 +215,12 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
-                    &h->keep_spc, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->keep_spc, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
   return 0;
 }
@@ -245,6 +251,7 @@ extern "C" int gckpp_gpu_set_option(gckpp_gpu_handle_t *h, const char *key, int 
   else if (!strcmp(key, "sort")) h->opt_sort = value;
   else if (!strcmp(key, "blocks_per_sm")) { if (value < 1 || value > 16) return fail(-10, "blocks_per_sm out of range"); h->blocks_per_sm = value; h->max_blocks = h->sm_count * value; }
   else if (!strcmp(key, "blocks_cap")) { h->sm_blocks_cap = value; }
+  else if (!strcmp(key, "chunks")) { if (value < 1 || value > 64) return fail(-10, "chunks out of range"); h->opt_chunks = value; }
   else if (!strcmp(key, "threads")) { if (value < 32 || value > 1024 || value % 32) return fail(-10, "threads must be a multiple of 32"); h->threads = value; }
   else return fail(-10, "gckpp_gpu_set_option: unknown option '%s'", key);
   return 0;
@@ -600,6 +607,115 @@ static int h2d(gckpp_gpu_handle *h, DevBuf &b, const void *src, size_t bytes)
   return 0;
 }
 
+
+// Host-buffer entry, pipelined: the cells are cut into `chunks` contiguous ranges; the slices of chunk i+1 are
+// copied to the device (copy-in stream) while chunk i integrates (handle stream) and the results of chunk i-1
+// travel back (copy-out stream).  Every per-cell array is [rows][ncell] cell-fastest, so a chunk is a 2-D copy
+// with pitch ncell*8.  Used when there is no `active` mask and no retry (those need the whole-grid lists).
+static int integrate_pipelined(gckpp_gpu_handle *h, int ncell, double tin, double tout,
+                               const double *conc_in, const double *rconst,
+                               const double *temp, const double *numden, const double *h2o,
+                               const double *photol, const double *khet,
+                               const double *atol, const double *rtol,
+                               const int32_t *icntrl, const double *rcntrl, const double *hstart,
+                               double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+{
+  const gckpp_host_tables_t *T = h->T;
+  const size_t nc = (size_t)ncell;
+  Decoded d;
+  int rc = decode_options(T, tin, tout, icntrl, rcntrl, atol, rtol, d);
+  if (rc) {
+    if (ierr && rc >= -5) for (size_t i = 0; i < nc; i++) ierr[i] = rc;
+    return rc;
+  }
+  if (d.autoreduce && d.ICNTRL[12] == 1) return fail(-12, "the append variant of auto-reduce (ICNTRL(13)=1) is not available in this build");
+  if (d.autoreduce && !T->fun_split) return fail(-12, "auto-reduce needs the split ODE function (fullchem)");
+  if (!rconst && (!temp || !numden || !h2o)) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
+  if (!h->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  if (!h->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
+  const bool have_ph = photol && T->nphot, have_kh = khet && T->next;
+  if (h->s_conc_in.ensure(sizeof(double) * T->nspec * nc) || h->s_conc_out.ensure(sizeof(double) * T->nspec * nc) ||
+      h->s_ist.ensure(sizeof(int) * 8 * nc) || h->s_rst.ensure(sizeof(double) * 4 * nc) || h->s_ierr.ensure(sizeof(int) * nc) ||
+      h->s_met.ensure(3 * sizeof(double) * nc) || (hstart && h->s_hstart.ensure(sizeof(double) * nc)) ||
+      (have_ph && h->s_photol.ensure(sizeof(double) * T->nphot * nc)) || (have_kh && h->s_khet.ensure(sizeof(double) * T->next * nc)) ||
+      (rconst ? h->s_rconst.ensure(sizeof(double) * T->nreact * nc) : h->rconst_work.ensure(sizeof(double) * T->nreact * nc)) ||
+      h->ident.ensure(sizeof(int) * nc))
+    return fail(-1002, "out of device memory");
+  if (h->ident_n < ncell) {
+    CUDA_TRY(launch_iota(h->ident.as<int>(), ncell, h->stream));
+    h->ident_n = ncell;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  double *d_temp = h->s_met.as<double>(), *d_numden = d_temp + nc, *d_h2o = d_numden + nc;
+  double *d_rc = rconst ? h->s_rconst.as<double>() : h->rconst_work.as<double>();
+  const int K = h->opt_chunks;
+  std::vector<cudaEvent_t> ev_in(K), ev_done(K);
+  for (int i = 0; i < K; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+  }
+  const size_t pitch = sizeof(double) * nc;
+  auto rows_in = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt, cudaStream_t st) {
+    return cudaMemcpy2DAsync((char *)dst + c0 * elt, nc * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows,
+                             cudaMemcpyHostToDevice, st);
+  };
+  auto rows_out = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt, cudaStream_t st) {
+    return cudaMemcpy2DAsync((char *)dst + c0 * elt, nc * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows,
+                             cudaMemcpyDeviceToHost, st);
+  };
+  (void)pitch;
+  CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+  // copy-in of every chunk is queued up front; the copy stream runs ahead of the compute stream
+  for (int i = 0; i < K; i++) {
+    const size_t c0 = nc * i / K, n = nc * (i + 1) / K - c0;
+    CUDA_TRY(rows_in(h->s_conc_in.p, conc_in, c0, n, T->nspec, 8, h->s_in));
+    if (rconst) CUDA_TRY(rows_in(h->s_rconst.p, rconst, c0, n, T->nreact, 8, h->s_in));
+    if (temp && numden && h2o) {
+      CUDA_TRY(rows_in(d_temp, temp, c0, n, 1, 8, h->s_in));
+      CUDA_TRY(rows_in(d_numden, numden, c0, n, 1, 8, h->s_in));
+      CUDA_TRY(rows_in(d_h2o, h2o, c0, n, 1, 8, h->s_in));
+    }
+    if (have_ph) CUDA_TRY(rows_in(h->s_photol.p, photol, c0, n, T->nphot, 8, h->s_in));
+    if (have_kh) CUDA_TRY(rows_in(h->s_khet.p, khet, c0, n, T->next, 8, h->s_in));
+    if (hstart) CUDA_TRY(rows_in(h->s_hstart.p, hstart, c0, n, 1, 8, h->s_in));
+    CUDA_TRY(cudaEventRecord(ev_in[i], h->s_in));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+  for (int i = 0; i < K; i++) {
+    const size_t c0 = nc * i / K, n = nc * (i + 1) / K - c0;
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_in[i], 0));
+    if (!rconst) {
+      CUDA_TRY(launch_update_rconst(h->mech_id, (int)n, d_temp + c0, d_numden + c0, d_h2o + c0,
+                                    have_ph ? h->s_photol.as<double>() + c0 : nullptr,
+                                    have_kh ? h->s_khet.as<double>() + c0 : nullptr, d_rc + c0, h->stream, ncell));
+      h->stats[6] += 1;
+    }
+    rc = run_integrator(h, d, ncell, (int)n, h->ident.as<int>() + c0, h->s_conc_in.as<double>(), d_rc,
+                        hstart ? h->s_hstart.as<double>() : nullptr, h->s_conc_out.as<double>(), h->s_ist.as<int32_t>(),
+                        h->s_rst.as<double>(), h->s_ierr.as<int32_t>());
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev_done[i], h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, ev_done[i], 0));
+    CUDA_TRY(rows_out(conc_out, h->s_conc_out.p, c0, n, T->nspec, 8, h->s_out));
+    if (istatus) CUDA_TRY(rows_out(istatus, h->s_ist.p, c0, n, 8, 4, h->s_out));
+    if (rstatus) CUDA_TRY(rows_out(rstatus, h->s_rst.p, c0, n, 4, 8, h->s_out));
+    if (ierr) CUDA_TRY(rows_out(ierr, h->s_ierr.p, c0, n, 1, 4, h->s_out));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+  unsigned long long sums[32];
+  CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->s_out));
+  for (int i = 0; i < K; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->stats[0] = ms; h->stats[9] = ms;
+  h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1]; h->stats[5] = 0;
+  return 0;
+}
+
 extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin, double tout,
                                    const double *conc_in, const double *rconst,
                                    const double *temp, const double *numden, const double *h2o,
@@ -616,6 +732,9 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
   const gckpp_host_tables_t *T = h->T;
   const size_t nc = (size_t)ncell;
   int rc;
+  if (!active && !h->opt_retry && h->opt_chunks > 1 && ncell >= 4096 * h->opt_chunks && T->nnz > 0)
+    return integrate_pipelined(h, ncell, tin, tout, conc_in, rconst, temp, numden, h2o, photol, khet, atol, rtol, icntrl,
+                               rcntrl, hstart, conc_out, istatus, rstatus, ierr);
   CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
   if ((rc = h2d(h, h->s_conc_in, conc_in, sizeof(double) * T->nspec * nc))) return rc;
   if (rconst && (rc = h2d(h, h->s_rconst, rconst, sizeof(double) * T->nreact * nc))) return rc;

@@ -23,18 +23,19 @@ __device__ __forceinline__ MetCell make_met(double temp, double numden, double h
 }
 
 template <int MECH>
-__global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, const double *__restrict__ temp,
+__global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int stride, const double *__restrict__ temp,
     const double *__restrict__ numden, const double *__restrict__ h2o, const double *__restrict__ photol,
     const double *__restrict__ khet, double *__restrict__ rconst)
 {
+  // ncell cells starting at the given pointers; rows of the cell-fastest arrays are `stride` apart
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ncell) return;
   MetCell m = make_met(temp[cell], numden[cell], h2o[cell]);
   const double *ph = photol ? photol + cell : nullptr;
   const double *kh = khet ? khet + cell : nullptr;
-  if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)ncell);
-  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)ncell);
-  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)ncell);
+  if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
+  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
+  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
 }
 
 __global__ void fill_int_kernel(int *p, int n, int v)
@@ -118,12 +119,23 @@ cudaError_t measure_fp64_peak(double *tflops, double *ms_out)
 
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,
-                                 double *rconst, cudaStream_t s)
+                                 double *rconst, cudaStream_t s, int stride)
 {
   int blocks = (ncell + 127) / 128;
-  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, temp, numden, h2o, photol, khet, rconst);
-  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, temp, numden, h2o, photol, khet, rconst);
-  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, temp, numden, h2o, photol, khet, rconst);
+  if (stride <= 0) stride = ncell;
+  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
+  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
+  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
+  return cudaGetLastError();
+}
+__global__ void iota_kernel(int *p, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+cudaError_t launch_iota(int *p, int n, cudaStream_t s)
+{
+  iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
   return cudaGetLastError();
 }
 cudaError_t launch_fill_int(int *p, int n, int v, cudaStream_t s)

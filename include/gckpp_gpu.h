@@ -64,6 +64,9 @@ int gckpp_gpu_finalize(gckpp_gpu_handle_t *handle);
  *                (bit-identical step sequences with the CPU restatement, any ICNTRL(3) method);
  *                1 = shared-memory-resident Rodas3 kernel (default for fullchem and Hg with
  *                ICNTRL(3) = 0 or 4; sums re-associated, FMA contraction, rounding-level differences)
+ *   "chunks"     host-buffer entry only: number of contiguous cell ranges whose host<->device copies are
+ *                overlapped with the integration of the neighbouring ranges (default 4; 1 = one serial pass).
+ *                Not used with an `active` mask or with "retry".
  *   "sort"       1 = visit cells in descending previous-step cost (hstart ascending); default 0
  */
 int gckpp_gpu_set_option(gckpp_gpu_handle_t *handle, const char *key, int value);

@@ -260,3 +260,23 @@ def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method):
     same = np.all(ist == isto, axis=0)
     print("method %d: mean Nstp %.1f, cells with different steps %d, max rel err %.3e" % (method, ist[2].mean(), int((~same).sum()), rel.max()))
     assert rel.max() <= 1e-4 and same.all()
+
+
+def test_pipelined_host_entry_matches_serial(solver):
+    """the host-buffer entry overlaps copies and compute over 4 cell ranges ("chunks"); results must be
+    bit-identical to the one-pass call (every cell is integrated independently of its neighbours)"""
+    g = grid.make_grid("4x5", limit=24001)
+    solver.set_option("kernel", 1)
+    args = (0.0, 1200.0, g["conc"], None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"])
+    kw = dict(hstart=g["hstart"], TEMP=g["temp"], NUMDEN=g["numden"], H2O=g["h2o"], PHOTOL=g["photol"], khet=g["khet"])
+    solver.set_option("chunks", 1)
+    c1, i1, r1, e1, _ = solver.Integrate(*args, **kw)
+    try:
+        for k in (4, 7):
+            solver.set_option("chunks", k)
+            c, i, r, e, _ = solver.Integrate(*args, **kw)
+            assert np.array_equal(c, c1) and np.array_equal(i, i1) and np.array_equal(r, r1) and np.array_equal(e, e1)
+            assert solver.last_stats()["cells"] == 24001
+    finally:
+        solver.set_option("chunks", 4)
+    assert (e1 == 1).all()
