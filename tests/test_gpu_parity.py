@@ -280,3 +280,38 @@ def test_pipelined_host_entry_matches_serial(solver):
     finally:
         solver.set_option("chunks", 4)
     assert (e1 == 1).all()
+
+
+@pytest.mark.parametrize("kernel", ["smem", "table"])
+@pytest.mark.parametrize("variant", ["non_autonomous", "scalar_tol", "clip_negative", "hmax_facmax"])
+def test_integrate_option_variants(solver, oracle, kernel, variant):
+    """the rest of the option surface Rosenbrock() decodes (gckpp_Integrator.F90:345-467): ICNTRL(1)=0 (the time
+    derivative is counted but zero because rates are frozen), ICNTRL(2)=1 scalar tolerances, ICNTRL(16)=1 clipping on
+    accept, RCNTRL(2)/(5) Hmax and FacMax"""
+    solver.set_option("kernel", KERNELS[kernel])
+    g = grid.make_grid("4x5", limit=20000)
+    rng = np.random.default_rng(17)
+    idx = np.sort(rng.choice(20000, 300, replace=False))
+    conc = np.ascontiguousarray(g["conc"][:, idx]); hs = g["hstart"][idx]
+    rc = oracle.update_rconst("fullchem", g["temp"][idx], g["numden"][idx], g["h2o"][idx],
+                              np.ascontiguousarray(g["photol"][:, idx]), np.ascontiguousarray(g["khet"][:, idx]))
+    icntrl, rcntrl, atol, rtol = g["icntrl"].copy(), g["rcntrl"].copy(), g["atol"].copy(), g["rtol"].copy()
+    if variant == "non_autonomous":
+        icntrl[0] = 0
+    elif variant == "scalar_tol":
+        icntrl[1] = 1
+        atol[:] = 1e-2; rtol[:] = 1e-2
+    elif variant == "clip_negative":
+        icntrl[15] = 1
+    else:
+        rcntrl[1], rcntrl[4] = 300.0, 2.0
+    co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, atol, rtol, icntrl, rcntrl, hstart=hs)
+    c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, atol, rtol, icntrl, rcntrl, hstart=hs)
+    assert np.array_equal(ierr, ierro)
+    rel = _parity(c, co)
+    same = np.all(ist == isto, axis=0)
+    print("%s/%s: cells with different steps %d, max rel err %.3e, mean Nstp %.1f" % (variant, kernel, int((~same).sum()), rel.max(), ist[2].mean()))
+    assert rel.max() <= 1e-4
+    assert same.all() if kernel == "table" else (~same).sum() <= 1
+    if variant == "clip_negative":
+        assert (c[:353] >= 0).all()
