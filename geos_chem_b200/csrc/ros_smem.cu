@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 
   // a streamed round: this warp's bundles arrive in order through its ring
   auto stream_round = [&](auto opc, unsigned d) {
-    const int nb = d & 0xfff, W = (d >> 12) & 15;
+    const int nb = DIR_NB(d), W = DIR_W(d);
     if (warp < W)
       for (int b = warp; b < nb; b += W) run_bundle<M, decltype(opc)::value>(rd, smem, slot, SCR);
   };
@@ -575,9 +575,9 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 #pragma unroll 1
         for (int r = 0; r < P.n_lu; r++) {
           const unsigned d = dir[P.o_lu + r];
-          if ((d >> 20) & 1) stream_round(std::integral_constant<int, OP_LUDIV>(), d);
+          if (DIR_DIV(d)) stream_round(std::integral_constant<int, OP_LUDIV>(), d);
           else stream_round(std::integral_constant<int, OP_LUUPD>(), d);
-          round_barrier((d >> 16) & 15, warp);
+          round_barrier(DIR_P(d), warp);
         }
         PROF(3);
         auto post_lu_row = [&](int i) {     // singular test (:1985), reciprocal diagonal, U row scaled by it
@@ -607,10 +607,10 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 #pragma unroll 1
           for (int r = 0; r < P.n_fwd; r++) {
             const unsigned d = dir[P.o_fwd1 + r];
-            const int nb = d & 0xfff, W = (d >> 12) & 15, wv = warp - NC;
+            const int nb = DIR_NB(d), W = DIR_W(d), wv = warp - NC;
             if (wv < W)
               for (int b = wv; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR);
-            asm volatile("bar.sync 12, %0;" :: "n"((NW - NC) * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"((NW - NC) * 32) : "memory");   // id 1: classes use ids 2..NW-1
           }
         }
         __syncthreads();
@@ -667,8 +667,8 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           d = 0; pr.n = 0; pr.p = RES + lane;
           if (r < n_tot) {
             d = dir[P.o_fwd + r];
-            if (warp < (int)((d >> 12) & 15)) {
-              const uint4 *p = RES + (size_t)boff[(d >> 21) + warp] * 32 + lane;
+            if (warp < DIR_W(d)) {
+              const uint4 *p = RES + (size_t)boff[DIR_BF(d) + warp] * 32 + lane;
               pr.c0 = p[0]; pr.c1 = p[32]; pr.p = p + 64;
             }
           }
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           if (r == P.n_fwd) tails();
           if (r == n_tot) break;
           const unsigned d = dn;
-          const int nb = d & 0xfff, W = (d >> 12) & 15, bf = d >> 21;
+          const int nb = DIR_NB(d), W = DIR_W(d), bf = DIR_BF(d);
           if (warp < W) {
             run_bundle<M, OP_SOLVE>(pn, smem, slot, SCR);
             for (int b = warp + W; b < nb; b += W) {       // only if a round has more bundles than warps
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           PROF(8);
           prefetch(r + 1, dn, pn);
           PROF(9);
-          round_barrier((d >> 16) & 15, warp);
+          round_barrier(DIR_P(d), warp);
           PROF(10);
         }
 #else
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           const unsigned d = dir[P.o_fwd + r];
 #ifdef SMEM_PROFILE
           {
-            const int nb = d & 0xfff, W = (d >> 12) & 15;
+            const int nb = DIR_NB(d), W = DIR_W(d);
             if (warp < W)
               for (int b = warp; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR, (tid == 0 && blockIdx.x == 0) ? pacc_ : nullptr);
           }
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           stream_round(std::integral_constant<int, OP_SOLVE>(), d);
 #endif
           PROF(8);
-          round_barrier((d >> 16) & 15, warp);
+          round_barrier(DIR_P(d), warp);
           PROF(10);
         }
 #endif
@@ -884,21 +884,21 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
     }
   }
   hp.resident.insert(hp.resident.end(), 128, 0u);      // the kernel prefetches one chunk row past a bundle
-  if (hp.boff.size() >= 2048 || hp.resident.size() / 128 >= 65536) return -4;
+  if (hp.boff.size() >= 1024 || hp.resident.size() / 128 >= 65536) return -4;
   hp.dir.assign(dr.size(), 0);
   for (size_t i = 0; i < dr.size(); i++) {
     int r = dr[i], nb = nbundles(r), W = nwarps(r);
-    if (nb >= 4096) return -4;
+    if (nb >= 2048) return -4;
     if ((int)i >= hp.o_fwd1) {            // warp-shifted rounds: at most NW-NC warps, their own barrier
       int Ws = nb < NW - NC ? nb : NW - NC;
-      hp.dir[i] = (uint32_t)nb | ((uint32_t)Ws << 12);
+      hp.dir[i] = DIR_PACK(nb, Ws, 0, 0, 0);
       continue;
     }
     bool last = ((int)i + 1 == hp.o_fwd1) || (int)i + 1 == hp.o_lu || (int)i + 1 == hp.o_fwd || (int)i + 1 == hp.o_bwd || i < 2;
     int Wn = last ? NW : nwarps(dr[i + 1]);
     int Pb = last ? NW : (W > Wn ? W : Wn);
     uint32_t div = (S->rounds[3 * r + 2] & 0x10) ? 1u : 0u;
-    hp.dir[i] = (uint32_t)nb | ((uint32_t)W << 12) | ((uint32_t)Pb << 16) | (div << 20) | ((uint32_t)bfirst[i] << 21);
+    hp.dir[i] = DIR_PACK(nb, W, Pb, div, bfirst[i]);
   }
   // per-warp streams in the order one Rodas3 attempt consumes them: vdot, jvs, lu rounds, [sweeps x2], vdot,
   // [sweeps], vdot, [sweeps]  (the sweeps only when their tables are not resident)

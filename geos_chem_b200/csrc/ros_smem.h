@@ -8,7 +8,9 @@
 #ifndef SMEM_NC
 #define SMEM_NC 3          // cells integrated in lock step by one thread block (measured on B200: 2 -> 156k, 3 -> 199k, 4 -> 160k cells/s)
 #endif
+#ifndef SMEM_NW
 #define SMEM_NW 12         // warps per block
+#endif
 // With 2 cells per block the tables of the triangular sweeps (used 4x per attempt) stay resident in shared
 // memory and the ring is 6 slots deep; with 3 cells the space goes to the third matrix and the sweep tables
 // are streamed like the others through a 4-slot ring.
@@ -37,6 +39,15 @@
 #define SMEM_SCR_GLOBAL 0
 #endif
 
+// round directory entry: bundles of the round, warps that work on it, warps that synchronise after it,
+// LU division round flag, first resident bundle
+#define DIR_NB(d) ((int)((d) & 0x7ffu))
+#define DIR_W(d) ((int)(((d) >> 11) & 31u))
+#define DIR_P(d) ((int)(((d) >> 16) & 31u))
+#define DIR_DIV(d) ((int)(((d) >> 21) & 1u))
+#define DIR_BF(d) ((int)((d) >> 22))
+#define DIR_PACK(nb, W, P, div, bf) ((uint32_t)(nb) | ((uint32_t)(W) << 11) | ((uint32_t)(P) << 16) | ((uint32_t)(div) << 21) | ((uint32_t)(bf) << 22))
+
 struct SmemArgs {
   // streamed tables (vdot, jvs, lu rounds): per-warp chunk rows in consumption order, cyclic per attempt
   const uint4 *stream;
@@ -44,7 +55,7 @@ struct SmemArgs {
   // resident tables (fwd, bwd rounds): copied to shared memory at kernel start
   const uint4 *resident; int res_rows;
   const uint16_t *boff; int nresb;        // first chunk row of every resident bundle
-  const uint32_t *dir; int ndir;          // round directory: nb | W<<12 | P<<16 | div<<20 | first resident bundle<<21
+  const uint32_t *dir; int ndir;          // round directory (DIR_* above)
   int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   const uint16_t *tpos;                   // [32][32]
   const uint16_t *diag, *crow;            // [nvar], [nvar+1]
