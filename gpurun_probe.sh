@@ -1,5 +1,3 @@
 #!/bin/bash
-( timeout 300 python tests/gpu_tools/smem_debug.py small ) 2>&1 | tail -3
-timeout 200 python tools/variant_bench.py own 2>&1 | tail -1
-GCKPP_B200_LIB=$PWD/geos_chem_b200/libvar_nw16.so timeout 300 python tests/gpu_tools/smem_debug.py small 2>&1 | tail -3
-GCKPP_B200_LIB=$PWD/geos_chem_b200/libvar_nw16.so timeout 200 python tools/variant_bench.py own 2>&1 | tail -1
+# ad-hoc GPU probe used during development
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
