@@ -7,7 +7,7 @@
 A "step" = one pass of the hot path (Update_RCONST + Integrate over every cell of the grid) on
 synthetic inputs (geos_chem_b200/grid.py).  N=1 is BASELINE config 2: 4x5 global, 72 levels,
 238,464 cells.  N>1 (launched with torchrun, one rank per GPU): every rank integrates its own
-4x5-sized block of columns of an N-times larger grid (weak scaling, no data-path collective;
+4x5-sized share of the columns of an N-times larger grid, dealt round-robin (weak scaling, no data-path collective;
 NCCL only reduces the step-count diagnostics).
 value = whole-job cells/s with inputs resident in HBM (device entry point);
 e2e   = the same through the host-buffer C-ABI call (pinned host arrays, H2D + D2H inside the timed region).
@@ -86,12 +86,10 @@ class ClockSampler:
 def make_inputs(args, rank, world):
     from geos_chem_b200 import grid
     NX, NY, NZ = grid.GRIDS[args.grid]
-    # weak scaling: the global grid is `world` times wider; rank r owns the r-th block of columns
+    # weak scaling: the global grid is `world` times wider; its (I,J) columns are dealt round-robin over the
+    # ranks (every level of a column stays on one GPU), so each rank sees the global day/night mix
     shape = (NX * world, NY, NZ)
-    cols = np.arange(NX * world * NY, dtype=np.int64)
-    I, J = cols % (NX * world), cols // (NX * world)
-    mine = cols[(I >= rank * NX) & (I < (rank + 1) * NX)]
-    cells = (mine[None, :] + (NX * world * NY) * np.arange(NZ, dtype=np.int64)[:, None]).reshape(-1)
+    cells = grid.column_shard(shape, rank, world)
     if args.cells:
         cells = cells[:: max(1, cells.shape[0] // args.cells)][: args.cells]
     g = grid.make_cells(cells, shape, hstart=args.hstart)
