@@ -1,4 +1,3 @@
 #!/bin/bash
 # ad-hoc GPU probe used during development
-( time timeout 900 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -6
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "carbon" 2>&1 | tail -8

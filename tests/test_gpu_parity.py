@@ -315,3 +315,25 @@ def test_integrate_option_variants(solver, oracle, kernel, variant):
     assert same.all() if kernel == "table" else (~same).sum() <= 1
     if variant == "clip_negative":
         assert (c[:353] >= 0).all()
+
+
+@pytest.mark.parametrize("icntrl16", [0, 1, 2])
+def test_carbon_forward_euler_vs_oracle(lib, oracle, icntrl16):
+    """carbon mechanism (config 5): one forward-Euler step over the interval with the ICNTRL(16) negativity handling
+    (KPP/carbon/gckpp_Integrator.F90:155-215).  Unpinned by the reference; bit-exact against the oracle."""
+    s = kpp.KppSolver("carbon", device=0, max_cells=4096)
+    d = s.dims
+    rng = np.random.default_rng(3)
+    n = 777
+    conc = 10.0 ** rng.uniform(4, 12, size=(d["nspec"], n))
+    rconst = 10.0 ** rng.uniform(-16, -9, size=(d["nreact"], n))
+    icntrl = np.zeros(20, np.int32); icntrl[[0, 14, 15]] = [1, -1, icntrl16]
+    rcntrl = np.zeros(20)
+    atol, rtol = np.full(d["nvar"], 1e-2), np.full(d["nvar"], 1e-2)
+    co, isto, rsto, ierro = oracle.integrate("carbon", 0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
+    c, ist, rst, ierr, _ = s.Integrate(0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
+    s.close()
+    assert np.array_equal(ierr, ierro) and np.array_equal(ist, isto)
+    assert np.array_equal(c, co)
+    if icntrl16 == 1:
+        assert (c[:d["nvar"]] >= 0).all()
