@@ -240,7 +240,7 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
 // column), so the pivot loop stays rolled and the code small enough for the instruction cache.
 // Entries outside the LU pattern are exact zeros and stay zero (fill-in closure).
 template <class M>
-__device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int lane)
+__device__ __forceinline__ bool tail_lu(double *Gc, const uint16_t *tposT, int lane)
 {
   constexpr int m = M::TAIL;
   double r[m];
@@ -250,13 +250,21 @@ __device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int l
     r[k] = (p != TNONE) ? Gc[p] : 0.0;
   }
   // The reciprocal of the next pivot is started as soon as its column has been updated (first batch),
-  // so its latency overlaps the rest of the row update.
+  // so its latency overlaps the rest of the row update.  The factors are stored in their final form:
+  // L multipliers, the reciprocal diagonal, and U entries scaled by the reciprocal diagonal of their row
+  // (lane i keeps 1/d_i from the step at which column i was the pivot).
   double rinv = 1.0 / __shfl_sync(FULLMASK, r[0], 0);
+  double myrd = 0.0;
+  bool sing = false;
 #pragma unroll 1
   for (int j = 0; j < m; j++) {
     const double l = (lane > j) ? r[0] * rinv : 0.0;
+    if (lane == j) {
+      myrd = rinv;
+      sing = !(fabs(r[0]) >= DBL_MIN);          // singular test of ros_PrepareMatrix, also catches NaN
+    }
     const unsigned p = tposT[j * 32 + lane];
-    if (p != TNONE) Gc[p] = (lane > j) ? l : r[0];         // column j is final: L multiplier, diagonal or U entry
+    if (p != TNONE) Gc[p] = (lane > j) ? l : (lane == j ? rinv : r[0] * myrd);
     // update column j+k and rotate it to slot k-1; shuffles issued in batches so their latency overlaps
 #pragma unroll
     for (int k0 = 1; k0 < m; k0 += 8) {
@@ -274,6 +282,7 @@ __device__ __forceinline__ void tail_lu(double *Gc, const uint16_t *tposT, int l
     }
     r[m - 1] = 0.0;
   }
+  return __any_sync(FULLMASK, sing && lane < m);
 }
 
 // forward chain on the tail rows: x_i -= L(i,j) x_j, j ascending.  The matrix entries do not depend on
@@ -601,7 +610,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         }
         __syncthreads();
         if (warp < NC) {
-          tail_lu<M>(G + warp * L::GS, tposT, lane);
+          if (tail_lu<M>(G + warp * L::GS, tposT, lane)) slot[warp].sing = 1;
         } else {
           for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) post_lu_row(i);
 #pragma unroll 1
@@ -613,14 +622,12 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
             asm volatile("bar.sync 1, %0;" :: "n"((NW - NC) * 32) : "memory");   // id 1: classes use ids 2..NW-1
           }
         }
-        __syncthreads();
-        PROF(4);
-        if (tid >= M::HEAD && tid < N) post_lu_row(tid);
+        PROF(4);        // the tail rows leave tail_lu in their final form; the stage loop's barrier orders everything
 #else
-        if (warp < NC) tail_lu<M>(G + warp * L::GS, tposT, lane);
+        if (warp < NC && tail_lu<M>(G + warp * L::GS, tposT, lane)) slot[warp].sing = 1;
         __syncthreads();
         PROF(4);
-        if (tid < N) post_lu_row(tid);
+        if (tid < M::HEAD) post_lu_row(tid);
 #endif
         PROF(5);
       }
