@@ -100,6 +100,7 @@ struct gckpp_gpu_handle {
   SmemArgs sargs{};
   DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
+  DevBuf sm_uscale;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -215,7 +216,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
-                    &h->keep_spc, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -423,7 +424,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
     {&h->sm_boff, p.boff.data(), p.boff.size() * 2},       {&h->sm_dir, p.dir.data(), p.dir.size() * 4},
     {&h->sm_tpos, S->tpos, 32 * 32 * 2},                   {&h->sm_diag, p.diag.data(), p.diag.size() * 2},
     {&h->sm_crow, p.crow.data(), p.crow.size() * 2},       {&h->sm_aw, p.aw.data(), p.aw.size() * 4},
-    {&h->sm_bw, p.bw.data(), p.bw.size() * 4},             {&h->sm_coefs, S->coefs, sizeof(double) * (size_t)S->ncoef},
+    {&h->sm_bw, p.bw.data(), p.bw.size() * 4},             {&h->sm_uscale, p.uscale.data(), p.uscale.size() * 4},             {&h->sm_coefs, S->coefs, sizeof(double) * (size_t)S->ncoef},
   };
   for (Up &u : ups) {
     if (u.b->ensure(u.bytes ? u.bytes : 16)) return fail(-1002, "out of device memory for the kernel tables");
@@ -440,6 +441,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
   A.diag = h->sm_diag.as<uint16_t>(); A.crow = h->sm_crow.as<uint16_t>();
   A.aw = h->sm_aw.as<uint32_t>(); A.bw = h->sm_bw.as<uint32_t>();
   A.coefs = h->sm_coefs.as<double>();
+  A.uscale = h->sm_uscale.as<uint32_t>(); A.nuscale = (int)p.uscale.size();
   A.lit = h->M.lit;
   if (h->sm_rcs.ensure(sizeof(double) * smem_rcs_doubles_per_block(h->mech_id) * (size_t)h->sm_count)) return fail(-1002, "out of device memory");
   A.rcs = h->sm_rcs.as<double>();

@@ -612,7 +612,24 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         if (warp < NC) {
           if (tail_lu<M>(G + warp * L::GS, tposT, lane)) slot[warp].sing = 1;
         } else {
-          for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) post_lu_row(i);
+          // head rows: reciprocal diagonals first, then every U entry of the head rows scaled by it, spread
+          // evenly over the threads (a thread per row would wait for the longest row)
+          for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
+            const int dp = diag[i];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+              const double d = G[c * L::GS + dp];
+              if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;
+              G[c * L::GS + dp] = 1.0 / d;
+            }
+          }
+          asm volatile("bar.sync 1, %0;" :: "n"((NW - NC) * 32) : "memory");
+          for (int q = tid - NC * 32; q < P.nuscale; q += NT - NC * 32) {
+            const unsigned w = __ldg(P.uscale + q);
+            const int p = w >> 16, dp = w & 0xffff;
+#pragma unroll
+            for (int c = 0; c < NC; c++) G[c * L::GS + p] *= G[c * L::GS + dp];
+          }
 #pragma unroll 1
           for (int r = 0; r < P.n_fwd; r++) {
             const unsigned d = dir[P.o_fwd1 + r];
@@ -947,6 +964,9 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   for (int r = 0; r < T->nreact; r++) encode_term(T->a_term + 4 * r, T->nreact, T->nspec, T->nlit, &hp.aw[2 * r]);
   hp.bw.resize(2 * (size_t)(T->nb > 0 ? T->nb : 1));
   for (int m = 0; m < T->nb; m++) encode_term(T->b_term + 4 * m, T->nreact, T->nspec, T->nlit, &hp.bw[2 * m]);
+  hp.uscale.clear();
+  for (int i = 0; i < S->head; i++)
+    for (int p = T->diag[i] + 1; p < T->crow[i + 1]; p++) hp.uscale.push_back(((uint32_t)p << 16) | (uint32_t)T->diag[i]);
   hp.diag.resize(T->nvar); hp.crow.resize(T->nvar + 1);
   for (int i = 0; i < T->nvar; i++) hp.diag[i] = (uint16_t)T->diag[i];
   for (int i = 0; i <= T->nvar; i++) hp.crow[i] = (uint16_t)T->crow[i];

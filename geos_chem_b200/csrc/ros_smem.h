@@ -59,6 +59,7 @@ struct SmemArgs {
   int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   const uint16_t *tpos;                   // [32][32]
   const uint16_t *diag, *crow;            // [nvar], [nvar+1]
+  const uint32_t *uscale; int nuscale;    // head rows: (position of a U entry) << 16 | position of its row's diagonal
   const uint32_t *aw, *bw;                // [nreact][2], [nb][2] encoded rate / partial-derivative terms
   const double *coefs;                    // [ncoef] stoichiometric coefficients (signed)
   const double *lit;                      // [nlit] literal pool
@@ -70,7 +71,7 @@ struct SmemArgs {
 
 struct SmemHostPlan {
   int warp_off[SMEM_NW], warp_rows[SMEM_NW];
-  std::vector<uint32_t> stream, resident, dir, aw, bw;
+  std::vector<uint32_t> stream, resident, dir, aw, bw, uscale;
   std::vector<uint16_t> boff, diag, crow;
   int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
