@@ -12,8 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 GEN = os.path.join(CSRC, "gen")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libgckpp_b200.so")
+# GCKPP_BUILD_TAG=<tag> builds a variant (other -D flags) into its own object directory and lib<...>_<tag>.so
+TAG = os.environ.get("GCKPP_BUILD_TAG", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libgckpp_b200%s.so" % ("_" + TAG if TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -25,6 +27,8 @@ UNITS = {
     "ros_generic.cu": ["-fmad=false"],
     # production kernel: shared-memory-resident, FMA allowed
     "ros_smem.cu": (["-DSMEM_PROFILE"] if os.environ.get("GCKPP_SMEM_PROFILE") else []) + os.environ.get("GCKPP_SMEM_DEFS", "").split(),
+    # production kernel: one warp per cell
+    "ros_warp.cu": (["-DWARP_PROFILE"] if os.environ.get("GCKPP_WARP_PROFILE") else []) + os.environ.get("GCKPP_WARP_DEFS", "").split(),
     "gckpp_gpu.cu": os.environ.get("GCKPP_SMEM_DEFS", "").split(),
 }
 

@@ -15,12 +15,15 @@
 #include "ros_common.cuh"
 #include "kernels.h"
 #include "ros_smem.h"
+#include "ros_warp.h"
 
 #include "gen/fullchem_tables.h"
 #include "gen/Hg_tables.h"
 #include "gen/carbon_tables.h"
 #include "gen/fullchem_sched.h"
 #include "gen/Hg_sched.h"
+#include "gen/fullchem_wsched.h"
+#include "gen/Hg_wsched.h"
 #include "gen/fullchem_names.h"
 #include "gen/Hg_names.h"
 #include "gen/carbon_names.h"
@@ -58,6 +61,15 @@ static const gckpp_sched_tables_t *host_sched(int mech_id)
   switch (mech_id) {
   case GCKPP_MECH_FULLCHEM: return &fullchem_sched;
   case GCKPP_MECH_HG: return &Hg_sched;
+  default: return nullptr;
+  }
+}
+
+static const gckpp_wsched_tables_t *host_wsched(int mech_id)
+{
+  switch (mech_id) {
+  case GCKPP_MECH_FULLCHEM: return &fullchem_wsched;
+  case GCKPP_MECH_HG: return &Hg_wsched;
   default: return nullptr;
   }
 }
@@ -101,6 +113,11 @@ struct gckpp_gpu_handle {
   DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
   int last_kernel = 0;
   DevBuf sm_uscale;
+  // warp-per-cell kernel: host plan + device copies of its tables
+  int w_ready = 0;
+  WarpHostPlan wplan;
+  WarpArgs wargs{};
+  DevBuf w_stream, w_aw, w_bw, w_diag, w_tpos, w_coefs, w_rcs;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -216,6 +233,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
   DevBuf *bufs[] = {&h->work, &h->next, &h->sums, &h->tol, &h->cell_list, &h->counter, &h->rconst_work, &h->scratch,
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
+                    &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
                     &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -453,15 +471,57 @@ static int prepare_smem(gckpp_gpu_handle *h)
   return 0;
 }
 
-// The shared-memory kernel implements the method GEOS-Chem selects (Rodas3, ICNTRL(3) = 0 or 4).
-static bool use_smem_kernel(gckpp_gpu_handle *h, const Decoded &d)
+// Upload the tables of the warp-per-cell kernel once per handle.
+static int prepare_warp(gckpp_gpu_handle *h)
 {
-  if (d.autoreduce) return false;            // auto-reduce runs on the table-driven kernel
-  if (h->opt_kernel == 0) return false;      // "kernel"=0 forces the table-driven, reference-order kernel
-  if (h->T->nnz <= 0 || !host_sched(h->mech_id) || !smem_kernel_supports(h->mech_id)) return false;
-  if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return false;
-  if (d.o.Tstart == d.o.Tend) return false;
-  return true;
+  if (h->w_ready) return 0;
+  const gckpp_wsched_tables_t *S = host_wsched(h->mech_id);
+  if (!S || !warp_kernel_supports(h->mech_id)) return fail(-11, "warp-per-cell kernel not available for this mechanism");
+  int prc = warp_plan_build(h->mech_id, h->T, S, h->wplan);
+  if (prc) return fail(-11, "warp-per-cell kernel: plan failed (%d)", prc);
+  WarpHostPlan &p = h->wplan;
+  int maxsm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if (maxsm < warp_smem_bytes(h->mech_id)) return fail(-11, "warp-per-cell kernel needs %d bytes of shared memory, device offers %d", warp_smem_bytes(h->mech_id), maxsm);
+  struct Up { DevBuf *b; const void *src; size_t bytes; };
+  Up ups[] = {
+    {&h->w_stream, p.stream.data(), p.stream.size() * 4}, {&h->w_aw, p.aw.data(), p.aw.size() * 4},
+    {&h->w_bw, p.bw.data(), p.bw.size() * 4},             {&h->w_diag, p.diag.data(), p.diag.size() * 2},
+    {&h->w_tpos, S->tpos, 32 * 32 * 2},                   {&h->w_coefs, S->coefs, sizeof(double) * (size_t)S->ncoef},
+  };
+  for (Up &u : ups) {
+    if (u.b->ensure(u.bytes ? u.bytes : 16)) return fail(-1002, "out of device memory for the kernel tables");
+    if (u.bytes) CUDA_TRY(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+  }
+  WarpArgs &A = h->wargs;
+  A.stream = h->w_stream.as<uint4>(); A.rows_total = p.rows_total;
+  for (int i = 0; i < 3; i++) A.off_vdot[i] = p.off_vdot[i];
+  for (int i = 0; i < 4; i++) { A.off_fwd[i] = p.off_fwd[i]; A.off_bwd[i] = p.off_bwd[i]; }
+  A.off_jvs = p.off_jvs; A.off_lu = p.off_lu;
+  for (int i = 0; i < 5; i++) A.nb[i] = p.nb[i];
+  A.tpos = h->w_tpos.as<uint16_t>(); A.diag = h->w_diag.as<uint16_t>();
+  A.aw = h->w_aw.as<uint32_t>(); A.bw = h->w_bw.as<uint32_t>();
+  A.coefs = h->w_coefs.as<double>(); A.lit = h->M.lit;
+  size_t nwarps = (size_t)h->sm_count * warp_cells_per_block(h->mech_id);
+  if (h->w_rcs.ensure(sizeof(double) * warp_rcs_doubles_per_warp(h->mech_id) * nwarps)) return fail(-1002, "out of device memory");
+  A.rcs = h->w_rcs.as<double>();
+  A.s_total = warp_smem_bytes(h->mech_id);
+  h->w_ready = 1;
+  return 0;
+}
+
+// Which integrator kernel serves this call: 2 = warp-per-cell (default for Rodas3, ICNTRL(3) = 0 or 4, the
+// method GEOS-Chem selects), 1 = the block-synchronous shared-memory kernel of round 1 (kept for comparison),
+// 0 = the table-driven reference-order kernel (every method, auto-reduce).
+static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
+{
+  if (d.autoreduce) return 0;                // auto-reduce runs on the table-driven kernel
+  if (h->opt_kernel == 0) return 0;          // "kernel"=0 forces the table-driven, reference-order kernel
+  if (h->T->nnz <= 0) return 0;
+  if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return 0;
+  if (d.o.Tstart == d.o.Tend) return 0;
+  if (h->opt_kernel == 1) return (host_sched(h->mech_id) && smem_kernel_supports(h->mech_id)) ? 1 : 0;
+  return (host_wsched(h->mech_id) && warp_kernel_supports(h->mech_id)) ? 2 : 0;
 }
 
 static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int nwork, const int *cell_list,
@@ -469,10 +529,11 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
                           double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
 {
   if (nwork <= 0) return 0;
-  const bool smem = use_smem_kernel(h, d);
+  const int kern = choose_kernel(h, d);
+  const bool smem = kern == 1;
   int blocks = (nwork + h->threads - 1) / h->threads;
   if (blocks > h->max_blocks) blocks = h->max_blocks;
-  int rc = smem ? prepare_smem(h) : ensure_workspace(h, blocks);
+  int rc = kern == 2 ? prepare_warp(h) : (smem ? prepare_smem(h) : ensure_workspace(h, blocks));
   if (rc) return rc;
   RosArgs a;
   a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
@@ -489,6 +550,13 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
   if (h->T->nnz == 0) {   // carbon: forward Euler
     CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
+  } else if (kern == 2) { // one persistent block per SM, one cell per warp
+    const int cpb = warp_cells_per_block(h->mech_id);
+    int nb = (nwork + cpb - 1) / cpb;
+    if (nb > h->sm_count) nb = h->sm_count;
+    if (h->sm_blocks_cap > 0 && nb > h->sm_blocks_cap) nb = h->sm_blocks_cap;
+    CUDA_TRY(launch_ros_warp(h->mech_id, h->wargs, a, nb, h->stream));
+    h->last_kernel = 2;
   } else if (smem) {      // one persistent block per SM, SMEM_NC cells each
     int nb = (nwork + SMEM_NC - 1) / SMEM_NC;
     if (nb > h->sm_count) nb = h->sm_count;
@@ -564,10 +632,15 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
   unsigned long long sums[32];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (getenv("GCKPP_PROFILE"))
-    fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
-            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
-            sums[20], sums[21], sums[22], sums[23]);
+  if (getenv("GCKPP_PROFILE")) {
+    if (h->last_kernel == 2)
+      fprintf(stderr, "[gckpp profile] warp 0 of block 0, cycles: load %llu fun0 %llu jac %llu lu_head %llu lu_tail %llu (unused %llu) stage_fun+rhs %llu solves(x4) %llu accept %llu retire %llu\n",
+              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17]);
+    else
+      fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
+              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
+              sums[20], sums[21], sums[22], sums[23]);
+  }
   int nfail = (int)sums[2], nfail2 = 0;
   h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
 

@@ -8,6 +8,8 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "own"
 g = grid.make_grid("4x5", hstart="warm")
 n = g["conc"].shape[1]
 s = kpp.KppSolver("fullchem", 0, max_cells=n)
+for kv in sys.argv[2:]:
+    k, v = kv.split("="); s.set_option(k, int(v))
 dev = torch.device("cuda:0")
 if "torchstream" in mode:
     s.set_stream(torch.cuda.current_stream().cuda_stream)
