@@ -216,7 +216,7 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
 #undef UP
   h->L = make_layout(T);
   h->max_blocks = h->sm_count * h->blocks_per_sm;
-  if (h->next.ensure(sizeof(int)) || h->sums.ensure(32 * sizeof(unsigned long long)) ||
+  if (h->next.ensure(sizeof(int)) || h->sums.ensure(64 * sizeof(unsigned long long)) ||
       h->tol.ensure(2 * sizeof(double) * T->nvar) || h->counter.ensure(4 * sizeof(int))) {
     gckpp_gpu_finalize(h);
     return fail(-1002, "gckpp_gpu_init: out of device memory");
@@ -494,16 +494,17 @@ static int prepare_warp(gckpp_gpu_handle *h)
     if (u.bytes) CUDA_TRY(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
   }
   WarpArgs &A = h->wargs;
-  A.stream = h->w_stream.as<uint4>(); A.rows_total = p.rows_total;
-  for (int i = 0; i < 3; i++) A.off_vdot[i] = p.off_vdot[i];
-  for (int i = 0; i < 4; i++) { A.off_fwd[i] = p.off_fwd[i]; A.off_bwd[i] = p.off_bwd[i]; }
-  A.off_jvs = p.off_jvs; A.off_lu = p.off_lu;
-  for (int i = 0; i < 5; i++) A.nb[i] = p.nb[i];
+  A.stream = h->w_stream.as<uint4>();
+  for (int w = 0; w < WARP_WG; w++) {
+    A.w_off[w] = p.w_off[w]; A.w_rows[w] = p.w_rows[w];
+    for (int i = 0; i < WARP_NSEG; i++) A.seg_off[w][i] = p.seg_off[w][i];
+    for (int i = 0; i < WARP_NPH; i++) A.nb[w][i] = p.nb[w][i];
+  }
   A.tpos = h->w_tpos.as<uint16_t>(); A.diag = h->w_diag.as<uint16_t>();
   A.aw = h->w_aw.as<uint32_t>(); A.bw = h->w_bw.as<uint32_t>();
   A.coefs = h->w_coefs.as<double>(); A.lit = h->M.lit;
-  size_t nwarps = (size_t)h->sm_count * warp_cells_per_block(h->mech_id);
-  if (h->w_rcs.ensure(sizeof(double) * warp_rcs_doubles_per_warp(h->mech_id) * nwarps)) return fail(-1002, "out of device memory");
+  size_t ngroups = (size_t)h->sm_count * warp_cells_per_block(h->mech_id);
+  if (h->w_rcs.ensure(sizeof(double) * warp_rcs_doubles_per_group(h->mech_id) * ngroups)) return fail(-1002, "out of device memory");
   A.rcs = h->w_rcs.as<double>();
   A.s_total = warp_smem_bytes(h->mech_id);
   h->w_ready = 1;
@@ -599,7 +600,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
 
   // K1: rate constants
   CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
@@ -629,13 +630,18 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
 
-  unsigned long long sums[32];
+  unsigned long long sums[64];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (getenv("GCKPP_PROFILE")) {
-    if (h->last_kernel == 2)
-      fprintf(stderr, "[gckpp profile] warp 0 of block 0, cycles: load %llu fun0 %llu jac %llu lu_head %llu lu_tail %llu (unused %llu) stage_fun+rhs %llu solves(x4) %llu accept %llu retire %llu\n",
-              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17]);
+    if (h->last_kernel == 2) {
+      fprintf(stderr, "[gckpp profile] lead warp of group 0, block 0, cycles: load %llu fun0(vdot) %llu jac %llu lu_head %llu lu_tail %llu tail_solve %llu stage_rhs+vdot %llu solve_streams %llu accept %llu retire %llu rates %llu\n",
+              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18]);
+      const char *kn[4] = {"vdot", "jvs", "lu", "solve"};
+      for (int k = 0; k < 4; k++)
+        fprintf(stderr, "[gckpp profile]   %-5s bundles %llu: table wait %llu operands+fma %llu shuffles %llu store %llu barrier %llu\n", kn[k],
+                sums[20 + 6 * k + 5], sums[20 + 6 * k + 0], sums[20 + 6 * k + 1], sums[20 + 6 * k + 2], sums[20 + 6 * k + 3], sums[20 + 6 * k + 4]);
+    }
     else
       fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
               sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
@@ -654,7 +660,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     Decoded d2 = d;
     d2.o.Hstart_rcntrl = 0.0;
-    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
     rc = run_integrator(h, d2, ncell, nretry, h->cell_list.as<int>(), conc_in, rconst, nullptr, conc_out, istatus, rstatus, ierr);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
@@ -723,7 +729,7 @@ static int integrate_pipelined(gckpp_gpu_handle *h, int ncell, double tin, doubl
   }
   CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
   double *d_temp = h->s_met.as<double>(), *d_numden = d_temp + nc, *d_h2o = d_numden + nc;
   double *d_rc = rconst ? h->s_rconst.as<double>() : h->rconst_work.as<double>();
   const int K = h->opt_chunks;
@@ -780,7 +786,7 @@ static int integrate_pipelined(gckpp_gpu_handle *h, int ncell, double tin, doubl
     if (ierr) CUDA_TRY(rows_out(ierr, h->s_ierr.p, c0, n, 1, 4, h->s_out));
   }
   CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-  unsigned long long sums[32];
+  unsigned long long sums[64];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->s_out));
@@ -994,6 +1000,36 @@ extern "C" int gckpp_gpu_plan_info(int mech_id, int32_t *info)
   if (rc) return fail(-11, "plan failed (%d)", rc);
   info[0] = p.s_total; info[1] = (int)(p.stream.size() / 128); info[2] = (int)(p.resident.size() / 128);
   info[3] = (int)p.dir.size(); info[4] = p.n_lu; info[5] = p.n_fwd; info[6] = p.n_bwd; info[7] = SMEM_NC;
+  return 0;
+}
+
+// Test hook: the per-warp table streams of the warp-group kernel as the host plan lays them out.
+//   info[0] = warps per group, info[1] = cells per block, info[2] = shared memory bytes, info[3] = total rows;
+//   then per warp-stream w (8 + WARP_NSEG + WARP_NPH ints each, starting at info[8]): w_off, w_rows, seg_off[], nb[].
+extern "C" int gckpp_gpu_warp_plan(int mech_id, int32_t *info, int info_cap, uint32_t *stream_out, int64_t stream_cap_words)
+{
+  const gckpp_host_tables_t *T = host_tables(mech_id);
+  const gckpp_wsched_tables_t *S = host_wsched(mech_id);
+  if (!T || !S || !info) return fail(-11, "no warp-group kernel plan for mechanism %d", mech_id);
+  WarpHostPlan p;
+  int rc = warp_plan_build(mech_id, T, S, p);
+  if (rc) return fail(-11, "plan failed (%d)", rc);
+  const int per = 2 + WARP_NSEG + WARP_NPH;
+  if (info_cap < 8 + WARP_WG * per) return fail(-10, "info too small");
+  int wg = 0;
+  for (int w = 0; w < WARP_WG; w++) if (p.w_rows[w] > 0) wg = w + 1;
+  info[0] = wg; info[1] = warp_cells_per_block(mech_id); info[2] = warp_smem_bytes(mech_id); info[3] = (int)(p.stream.size() / 128);
+  info[4] = WARP_NSEG; info[5] = WARP_NPH; info[6] = WARP_RS; info[7] = per;
+  for (int w = 0; w < wg; w++) {
+    int32_t *o = info + 8 + w * per;
+    o[0] = p.w_off[w]; o[1] = p.w_rows[w];
+    for (int i = 0; i < WARP_NSEG; i++) o[2 + i] = p.seg_off[w][i];
+    for (int i = 0; i < WARP_NPH; i++) o[2 + WARP_NSEG + i] = p.nb[w][i];
+  }
+  if (stream_out) {
+    if ((int64_t)p.stream.size() > stream_cap_words) return fail(-10, "stream buffer too small");
+    memcpy(stream_out, p.stream.data(), p.stream.size() * 4);
+  }
   return 0;
 }
 

@@ -46,6 +46,19 @@
 #define WPROF_DECL
 #define WPROF(i) do { } while (0)
 #endif
+// bundle-level profile (WARP_PROFILE): the dependent "sink" makes the in-order issue wait for the value first
+#ifdef WARP_PROFILE
+#define BSINK32(v) asm volatile("xor.b32 %0, %0, %1;" : "+r"(bsink_) : "r"(v))
+#define BSINKD(v) asm volatile("xor.b32 %0, %0, %1;" : "+r"(bsink_) : "r"(__double2loint(v)))
+#define BPROF(i) do { if (bp) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)); bp[i] += t_ - bt_; bt_ = t_; } } while (0)
+#else
+#define BSINK32(v) do { } while (0)
+#define BSINKD(v) do { } while (0)
+#define BPROF(i) do { } while (0)
+#endif
+#ifndef WARP_FAST_RCP
+#define WARP_FAST_RCP 1       // pivot reciprocals: MUFU approximation + 2 Newton steps (1) or IEEE division (0)
+#endif
 
 namespace {
 
@@ -54,37 +67,56 @@ constexpr unsigned TNONE = 0xFFFFu;
 constexpr unsigned F_SYNC = 1u << 9, F_WRITE = 1u << 10, F_MUL = 1u << 11, F_DIAG = 1u << 12;
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per block on sm_100
 
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
-constexpr int cmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int a128(int x) { return (x + 127) & ~127; }
 
-template <class M, int MAXW>
-struct WLayT {
+// warps per cell: the big mechanism is spread over a group of warps, the small one (everything is "tail") is not
+template <class M> struct GroupOf { static constexpr int WG = WARP_WG; };
+template <> struct GroupOf<Hg_dims> { static constexpr int WG = 1; };
+
+struct GCtl {                 // per-group control words in shared memory
+  double red[8];
+  int cell, sing, pad_[2];
+};
+
+template <class M>
+struct WLay {
+  static constexpr int WG = GroupOf<M>::WG, GT = WG * 32;
   static constexpr int NYG = M::NSPEC + M::NLIT + 1;       // [VAR, FIX, literals, 1.0]
-  static constexpr int NSCR = cmax(M::NREACT, M::NB);
+  static constexpr int NSCR = M::NREACT;                   // A(r), or one half of B(m)
+  static_assert(M::NB <= 2 * M::NREACT, "B(m) is evaluated in two halves");
   // block-shared tables
   static constexpr int oCOEF = 0;
   static constexpr int oTPOS = a128(M::NCOEF * 8);
   static constexpr int oDIAG = oTPOS + 32 * 32 * 2;
-  static constexpr int oWARP = a128(oDIAG + M::NVAR * 2);
-  // one warp's slice (every array 128-byte aligned: the bank analysis of wsched.py is relative to that)
-  static constexpr int wG = 0;
-  static constexpr int wYG = a128((M::NNZ + 1) * 8);
-  static constexpr int wX = wYG + a128(NYG * 8);
-  static constexpr int wSCR = wX + a128(M::NVAR * 8);
-  static constexpr int wRING = wSCR + a128(NSCR * 8);
-  static constexpr int WSZ = wRING + RS * 512;
-  static constexpr int NWB = cmin(MAXW, (SMEM_LIMIT - oWARP) / WSZ);
-  static constexpr int TOTAL = oWARP + NWB * WSZ;
-  static constexpr int NQ = (M::NSPEC + 31) / 32;
+  static constexpr int oGRP = a128(oDIAG + M::NVAR * 2);
+  // one group's slice (every array 128-byte aligned: the bank analysis of wsched.py is relative to that)
+  static constexpr int gG = 0;
+  static constexpr int gYG = a128((M::NNZ + 1) * 8);
+  static constexpr int gX = gYG + a128(NYG * 8);
+  static constexpr int XPAD = cmax(M::NVAR, 64);           // X[XPAD] = 0.0, the operand of padding terms (never written)
+  static constexpr int gSCR = gX + a128((XPAD + 1) * 8);   // X[0..63] doubles as the pivot-row buffer of tail_lu
+  static constexpr int gCTL = gSCR + a128(NSCR * 8);
+  static constexpr int gRING = gCTL + a128((int)sizeof(GCtl));
+  static constexpr int GSZ = gRING + WG * RS * 512;
+  static constexpr int NGRP = cmin(cmin(1024 / GT, WG == 1 ? 16 : 15), (SMEM_LIMIT - oGRP) / GSZ);
+  static constexpr int TOTAL = oGRP + NGRP * GSZ;
+  static constexpr int NQ = (M::NSPEC + GT - 1) / GT;
 };
-template <class M> struct WLay : WLayT<M, 16> {};
 
 enum { K_VDOT, K_JVS, K_LU, K_SOLVE };
 
+template <int WG>
+__device__ __forceinline__ void gsync(int group)
+{
+  if (WG == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(WG * 32) : "memory");
+}
+
 // ---- streamed tables: 16 bytes per lane per row, cp.async ring ----------------------------------------
 struct WReader {
-  const uint4 *gsrc;        // this lane's column of the stream
+  const uint4 *gsrc;        // this lane's column of the warp's stream
   uint32_t ring;            // shared-space byte address of this lane's column of the warp's ring
   int L, irow, islot, cslot, pos;
   __device__ __forceinline__ void issue()
@@ -120,108 +152,171 @@ struct WReader {
 struct WCtx {
   unsigned char *Gb, *Xb, *Sb;
   const unsigned char *Cb;
+  GCtl *ctl;
   double ghinv;
-  bool sing;
+  int group;
 };
 
 __device__ __forceinline__ double ldb(const unsigned char *base, unsigned off) { return *reinterpret_cast<const double *>(base + off); }
 __device__ __forceinline__ void stb(unsigned char *base, unsigned off, double v) { *reinterpret_cast<double *>(base + off) = v; }
 
-// nb bundles of one phase: every lane applies exactly T terms, partial sums of a split row are combined by a
-// segmented shuffle, the lane that owns the target finishes it.
-template <int KIND>
-__device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c)
+// reciprocal for the pivot chains: hardware approximation + two Newton steps (full double accuracy up to the last
+// ulp; ~55 cycles instead of ~90 for the IEEE division).  A zero pivot gives Inf/NaN, which the singular test catches.
+__device__ __forceinline__ double rcp_fast(double x)
 {
+#if WARP_FAST_RCP
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// nb bundles of one phase from this warp's stream: every lane applies exactly T terms (all operand loads of
+// a bundle are issued before its FMAs), partial sums of a split row are combined by a segmented shuffle, the
+// lane that owns the target finishes it; a bundle that ends a dependency level is followed by the group barrier.
+template <int KIND, int WG>
+#ifdef WARP_PROFILE
+__device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c, long long *bp = nullptr)
+#else
+__device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c)
+#endif
+{
+#ifdef WARP_PROFILE
+  unsigned bsink_ = 0;
+  long long bt_;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(bt_));
+#endif
   const unsigned char *Hb = (KIND == K_VDOT || KIND == K_JVS) ? c.Cb : c.Gb;
   const unsigned char *Lb = (KIND == K_VDOT || KIND == K_JVS) ? c.Sb : (KIND == K_LU ? c.Gb : c.Xb);
   unsigned char *Tb = (KIND == K_VDOT || KIND == K_SOLVE) ? c.Xb : c.Gb;
 #pragma unroll 1
   for (int b = 0; b < nb; b++) {
-    uint4 r = rd.next();
-    const unsigned hdr = r.x, meta = r.y;
+    const uint4 r0 = rd.next();
+    const unsigned hdr = r0.x, meta = r0.y;
     const int T = meta & 63, lg = (meta >> 6) & 7;
-    if (meta & F_SYNC) __syncwarp();
     const bool wr = (meta & F_WRITE) != 0;
+    BSINK32(meta); BPROF(0);
     double old = 0.0, mul = 1.0;
-    if (KIND == K_LU || KIND == K_SOLVE) {
+    if (KIND != K_VDOT) {
       if (wr) old = ldb(Tb, hdr & 0xffffu);
-      if (wr && (meta & F_MUL)) mul = ldb(c.Gb, hdr >> 16);
+      if (KIND != K_JVS && wr && (meta & F_MUL)) mul = ldb(c.Gb, hdr >> 16);
     }
-    double a0 = 0.0, a1 = 0.0;
-    if (T > 0) a0 = fma(ldb(Hb, r.z >> 16), ldb(Lb, r.z & 0xffffu), a0);
-    if (T > 1) a1 = fma(ldb(Hb, r.w >> 16), ldb(Lb, r.w & 0xffffu), a1);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#define LDT(w, hv, lv) const double hv = ldb(Hb, (w) >> 16), lv = ldb(Lb, (w) & 0xffffu)
+#define LDP(p, w, hv, lv) double hv = 0.0, lv = 0.0; if (p) { hv = ldb(Hb, (w) >> 16); lv = ldb(Lb, (w) & 0xffffu); }
+    if (T <= 2) {                       // one table row
+      LDP(T > 0, r0.z, h0, l0) LDP(T > 1, r0.w, h1, l1)
+      a0 = h0 * l0; a1 = h1 * l1;
+    } else if (T <= 6) {                // two table rows
+      const uint4 r1 = rd.next();
+      LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2);
+      LDP(T > 3, r1.y, h3, l3) LDP(T > 4, r1.z, h4, l4) LDP(T > 5, r1.w, h5, l5)
+      a0 = h0 * l0; a1 = h1 * l1; a2 = h2 * l2; a3 = h3 * l3;
+      a0 = fma(h4, l4, a0); a1 = fma(h5, l5, a1);
+    } else {                            // three table rows, and a loop for the rare longer lane
+      const uint4 r1 = rd.next();
+      uint4 r2 = rd.next();
+      LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2); LDT(r1.y, h3, l3); LDT(r1.z, h4, l4); LDT(r1.w, h5, l5);
+      LDT(r2.x, h6, l6);
+      LDP(T > 7, r2.y, h7, l7) LDP(T > 8, r2.z, h8, l8) LDP(T > 9, r2.w, h9, l9)
+      a0 = h0 * l0; a1 = h1 * l1; a2 = h2 * l2; a3 = h3 * l3;
+      a0 = fma(h4, l4, a0); a1 = fma(h5, l5, a1); a2 = fma(h6, l6, a2); a3 = fma(h7, l7, a3);
+      a0 = fma(h8, l8, a0); a1 = fma(h9, l9, a1);
 #pragma unroll 1
-    for (int k = 2; k < T; k += 4) {
-      r = rd.next();
-      a0 = fma(ldb(Hb, r.x >> 16), ldb(Lb, r.x & 0xffffu), a0);
-      if (k + 1 < T) a1 = fma(ldb(Hb, r.y >> 16), ldb(Lb, r.y & 0xffffu), a1);
-      if (k + 2 < T) a0 = fma(ldb(Hb, r.z >> 16), ldb(Lb, r.z & 0xffffu), a0);
-      if (k + 3 < T) a1 = fma(ldb(Hb, r.w >> 16), ldb(Lb, r.w & 0xffffu), a1);
+      for (int k = 10; k < T; k += 4) {
+        r2 = rd.next();
+        LDT(r2.x, g0, m0);
+        LDP(k + 1 < T, r2.y, g1, m1) LDP(k + 2 < T, r2.z, g2, m2) LDP(k + 3 < T, r2.w, g3, m3)
+        a0 = fma(g0, m0, a0); a1 = fma(g1, m1, a1); a2 = fma(g2, m2, a2); a3 = fma(g3, m3, a3);
+      }
     }
-    double acc = a0 + a1;
+#undef LDT
+#undef LDP
+    double acc = (a0 + a1) + (a2 + a3);
+    BSINKD(acc); BPROF(1);
     for (int s = 0; s < lg; s++) acc += __shfl_down_sync(FULLMASK, acc, 1 << s);
+    BSINKD(acc); BPROF(2);
     if (wr) {
       const unsigned t = hdr & 0xffffu;
       if (KIND == K_VDOT) {
         stb(Tb, t, acc);
       } else if (KIND == K_JVS) {
-        stb(Tb, t, ((meta & F_DIAG) ? c.ghinv : 0.0) - acc);
+        stb(Tb, t, (old - acc) + ((meta & F_DIAG) ? c.ghinv : 0.0));
       } else {
         double v = (old - acc) * mul;
         if (KIND == K_LU && (meta & F_DIAG)) {
-          if (!(fabs(v) >= DBL_MIN)) c.sing = true;      // singular test of ros_PrepareMatrix, also catches NaN
-          v = 1.0 / v;
+          if (!(fabs(v) >= DBL_MIN)) c.ctl->sing = 1;      // singular test of ros_PrepareMatrix, also catches NaN
+          v = rcp_fast(v);
         }
         stb(Tb, t, v);
       }
     }
+    BPROF(3);
+    if (meta & F_SYNC) gsync<WG>(c.group);
+    BPROF(4);
   }
-  __syncwarp();
+#ifdef WARP_PROFILE
+  if (bp) { bp[5] += nb; if (bsink_ == 0x12345678u) bp[5]++; }
+#endif
 }
 
 // ---- tail block ------------------------------------------------------------------------------------------
-// Dense right-looking LU of the Schur complement: lane i holds row i in registers, the pivot row is
-// broadcast with shuffles.  The row registers ROTATE by one column per pivot (r[0] is always the pivot
-// column), so the pivot loop stays rolled.  Entries outside the LU pattern are exact zeros and stay zero
-// (fill-in closure).  The factors are stored in their final form: L multipliers, the reciprocal diagonal,
-// and U entries scaled by the reciprocal diagonal of their row.
+// Dense right-looking LU of the Schur complement by ONE warp: lane i holds row i in registers r[0..m-1].  The pivot
+// loop is fully unrolled (static register indices, no rotation); the pivot row is published by its owner lane
+// through a double-buffered shared-memory row and read back as broadcasts; the reciprocal of the NEXT pivot is
+// started as soon as its entry has been updated, so it overlaps the rest of the row update.  Entries outside the
+// LU pattern are exact zeros and stay zero (fill-in closure).  The factors are stored in their final form:
+// L multipliers, the reciprocal diagonal, and U entries scaled by the reciprocal diagonal of their row.
 template <class M>
-__device__ __forceinline__ bool tail_lu(double *Gc, const uint16_t *tposT, int lane)
+__device__ __forceinline__ bool tail_lu(double *Gc, double *buf, const uint16_t *tposT, int lane)
 {
   constexpr int m = M::TAIL;
+  static_assert(m % 2 == 0, "pairs of columns");
   double r[m];
 #pragma unroll
   for (int k = 0; k < m; k++) {
     const unsigned p = tposT[k * 32 + lane];
     r[k] = (p != TNONE) ? Gc[p] : 0.0;
   }
-  double rinv = 1.0 / __shfl_sync(FULLMASK, r[0], 0);
+  double rinv = rcp_fast(__shfl_sync(FULLMASK, r[0], 0));
   double myrd = 0.0;
   bool sing = false;
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < m; j++) {
-    const double l = (lane > j) ? r[0] * rinv : 0.0;
+    double *pb = buf + (j & 1) * m;
+    if (j < m - 1) {
+      if (lane == j) {
+#pragma unroll
+        for (int k = (j + 1) & ~1; k < m; k += 2) reinterpret_cast<double2 *>(pb)[k >> 1] = make_double2(r[k], r[k + 1]);
+      }
+      __syncwarp();
+    }
     if (lane == j) {
       myrd = rinv;
-      sing = !(fabs(r[0]) >= DBL_MIN);
+      sing = !(fabs(r[j]) >= DBL_MIN);
     }
-    const unsigned p = tposT[j * 32 + lane];
-    if (p != TNONE) Gc[p] = (lane > j) ? l : (lane == j ? rinv : r[0] * myrd);
+    const double l = (lane > j) ? r[j] * rinv : 0.0;
+    if (lane > j) r[j] = l;
+    if (j < m - 1) {
+      r[j + 1] = fma(-l, pb[j + 1], r[j + 1]);
+      rinv = rcp_fast(__shfl_sync(FULLMASK, r[j + 1], j + 1));
 #pragma unroll
-    for (int k0 = 1; k0 < m; k0 += 8) {
-      int hi[8], lo[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (k0 + q < m) {
-          hi[q] = __shfl_sync(FULLMASK, __double2hiint(r[k0 + q]), j);
-          lo[q] = __shfl_sync(FULLMASK, __double2loint(r[k0 + q]), j);
-        }
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (k0 + q < m) r[k0 + q - 1] = fma(-l, __hiloint2double(hi[q], lo[q]), r[k0 + q]);
-      if (k0 == 1) rinv = 1.0 / __shfl_sync(FULLMASK, r[0], (j + 1) & 31);
+      for (int k = (j + 2) & ~1; k < m; k += 2) {
+        const double2 u = reinterpret_cast<const double2 *>(pb)[k >> 1];
+        if (k >= j + 2) r[k] = fma(-l, u.x, r[k]);
+        r[k + 1] = fma(-l, u.y, r[k + 1]);
+      }
     }
-    r[m - 1] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < m; k++) {
+    const unsigned p = tposT[k * 32 + lane];
+    if (p != TNONE) Gc[p] = (k < lane) ? r[k] : (k == lane ? myrd : r[k] * myrd);
   }
   return __any_sync(FULLMASK, sing && lane < m);
 }
@@ -267,73 +362,118 @@ __device__ __forceinline__ void tail_solve(const double *Gc, double *Xc, const u
   if (lane < m) Xc[M::HEAD + lane] = x;
 }
 
+// SCR[i - i0] = rate(i) * YG[f1] * YG[f2] * YG[f3] for the items i0 <= i < i1 owned by this thread (i = i0 + gtid + k*GT).
+// The table words and rate constants of up to CH items are loaded before the first product (L2 latency paid once).
+template <int GT, int CH>
+__device__ __forceinline__ void eval_terms(const uint2 *__restrict__ wt, const double *__restrict__ rcs, const double *YG, double *SCR,
+                                           int i0, int i1, int gtid)
+{
+#pragma unroll 1
+  for (int base = i0 + gtid; base < i1; base += CH * GT) {
+    uint2 w[CH];
+    double rc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const int i = base + k * GT;
+      if (i < i1) { w[k] = __ldg(wt + i); rc[k] = __ldcg(rcs + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const int i = base + k * GT;
+      if (i < i1) SCR[i - i0] = rc[k] * YG[w[k].x >> 16] * YG[w[k].y & 0xffff] * YG[w[k].y >> 16];
+    }
+  }
+}
+
 template <class M>
-__global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs P, RosArgs a)
+__global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kernel(WarpArgs P, RosArgs a)
 {
   using L = WLay<M>;
-  constexpr int N = M::NVAR, NQ = L::NQ;
+  constexpr int N = M::NVAR, NQ = L::NQ, WG = L::WG, GT = L::GT;
   extern __shared__ __align__(128) unsigned char smem[];
   double *COEF = reinterpret_cast<double *>(smem + L::oCOEF);
   uint16_t *tposT = reinterpret_cast<uint16_t *>(smem + L::oTPOS);
   uint16_t *diag = reinterpret_cast<uint16_t *>(smem + L::oDIAG);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int group = warp / WG, wig = warp % WG, gtid = tid - group * GT;
+  // stream index of this warp: group g's LEAD warp (stream 0: narrow levels, tail chains) is its warp g % WG,
+  // so the lead warps of the groups of a block sit on different SM sub-partitions
+  const int sw = (wig + WG - group % WG) % WG;
+  const bool lead = sw == 0;
   for (int i = tid; i < M::NCOEF; i += blockDim.x) COEF[i] = P.coefs[i];
   for (int i = tid; i < 32 * 32; i += blockDim.x) tposT[i] = P.tpos[i];
   for (int i = tid; i < N; i += blockDim.x) diag[i] = P.diag[i];
-  unsigned char *wb = smem + L::oWARP + warp * L::WSZ;
-  double *G = reinterpret_cast<double *>(wb + L::wG);        // [NNZ+1]
-  double *YG = reinterpret_cast<double *>(wb + L::wYG);      // [NYG] state under evaluation + literals + 1.0
-  double *X = reinterpret_cast<double *>(wb + L::wX);        // [NVAR] right-hand side / solution
-  double *SCR = reinterpret_cast<double *>(wb + L::wSCR);    // [NSCR] A(r) or B(m)
-  for (int k = lane; k < L::NYG; k += 32)
+  unsigned char *gb = smem + L::oGRP + group * L::GSZ;
+  double *G = reinterpret_cast<double *>(gb + L::gG);        // [NNZ+1]
+  double *YG = reinterpret_cast<double *>(gb + L::gYG);      // [NYG] state under evaluation + literals + 1.0
+  double *X = reinterpret_cast<double *>(gb + L::gX);        // [NVAR] right-hand side / solution
+  double *SCR = reinterpret_cast<double *>(gb + L::gSCR);    // [NSCR] A(r) or half of B(m)
+  GCtl *ctl = reinterpret_cast<GCtl *>(gb + L::gCTL);
+  for (int k = gtid; k < L::NYG; k += GT)
     YG[k] = (k < M::NSPEC) ? 1.0 : (k < M::NSPEC + M::NLIT ? P.lit[k - M::NSPEC] : 1.0);
-  for (int k = lane; k <= M::NNZ; k += 32) G[k] = 0.0;
+  for (int k = gtid; k <= M::NNZ; k += GT) G[k] = 0.0;
+  if (gtid == 0) { ctl->cell = -1; ctl->sing = 0; X[L::XPAD] = 0.0; }
   __syncthreads();           // the only block barrier: the shared tables are in place
 
   const RosOpts &o = a.o;
   const double Dir = (double)o.Direction;
-  const int gwarp = blockIdx.x * L::NWB + warp;
-  double *rcsA = P.rcs + (size_t)gwarp * (M::NREACT + M::NB);     // rate constants of the cell in A(r) order
+  const int ggroup = blockIdx.x * L::NGRP + group;
+  double *rcsA = P.rcs + (size_t)ggroup * (M::NREACT + M::NB);    // rate constants of the cell in A(r) order
   double *rcsB = rcsA + M::NREACT;                                  // ... and in B(m) order
   const uint2 *awt = reinterpret_cast<const uint2 *>(P.aw), *bwt = reinterpret_cast<const uint2 *>(P.bw);
 
   WCtx c;
-  c.Gb = wb + L::wG; c.Xb = wb + L::wX; c.Sb = wb + L::wSCR; c.Cb = smem + L::oCOEF;
-  c.ghinv = 0.0; c.sing = false;
+  c.Gb = gb + L::gG; c.Xb = gb + L::gX; c.Sb = gb + L::gSCR; c.Cb = smem + L::oCOEF;
+  c.ctl = ctl; c.ghinv = 0.0; c.group = group;
   WReader rd;
-  rd.gsrc = P.stream + lane;
-  rd.ring = (uint32_t)__cvta_generic_to_shared(wb + L::wRING + lane * 16);
-  rd.L = P.rows_total;
+  rd.gsrc = P.stream + (size_t)P.w_off[sw] * 32 + lane;
+  rd.ring = (uint32_t)__cvta_generic_to_shared(gb + L::gRING + (wig * RS) * 512 + lane * 16);
+  rd.L = P.w_rows[sw];
   rd.seek(0);
+  int nbp[WARP_NPH], sof[WARP_NSEG];
+#pragma unroll
+  for (int i = 0; i < WARP_NPH; i++) nbp[i] = P.nb[sw][i];
+#pragma unroll
+  for (int i = 0; i < WARP_NSEG; i++) sof[i] = P.seg_off[sw][i];
 
   unsigned long long acc_stp = 0, acc_acc = 0, acc_fail = 0, acc_done = 0;
   WPROF_DECL
+#ifdef WARP_PROFILE
+  long long bacc_[4][6] = {};
+  const bool prof_ = (tid == 0 && blockIdx.x == 0);
+#define BP(k) , (prof_ ? bacc_[k] : nullptr)
+#else
+#define BP(k)
+#endif
 
-  // X = Fun(YG): A(r) = RCT(r) * prod(V) by the lane that owns reaction r, then the vdot stream
-  auto fun = [&](int which) {
-#pragma unroll 2
-    for (int r = lane; r < M::NREACT; r += 32) {
-      const uint2 w = __ldg(awt + r);
-      const double rc = __ldcg(rcsA + r);
-      SCR[r] = rc * YG[w.x >> 16] * YG[w.y & 0xffff] * YG[w.y >> 16];
-    }
-    rd.at(P.off_vdot[which]);
-    run_phase<K_VDOT>(rd, P.nb[WP_VDOT], c);
+  // X = Fun(YG): A(r) = RCT(r) * prod(V) by the thread that owns reaction r, then the vdot stream.
+  // YG must be visible to the group on entry; X is visible on return.
+  auto fun = [&](int seg) {
+    eval_terms<GT, 9>(awt, rcsA, YG, SCR, 0, M::NREACT, gtid);
+    gsync<WG>(group);
+    WPROF(10);
+    rd.at(sof[seg]);
+    run_phase<K_VDOT, WG>(rd, nbp[WP_VDOT], c BP(0));
   };
-  // KppSolve on X in place
-  auto solve = [&](int which) {
+  // KppSolve on X in place (X visible to the group on entry and on return)
+  auto solve = [&](int st) {
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-      rd.at(half ? P.off_bwd[which] : P.off_fwd[which]);
-      run_phase<K_SOLVE>(rd, P.nb[half ? WP_BWD : WP_FWD], c);
-      if (half == 0) tail_solve<M>(G, X, tposT, diag, lane);
+      rd.at(sof[WS_FWD0 + (st < 2 ? 2 * st : 3 * st - 1) + half]);
+      run_phase<K_SOLVE, WG>(rd, nbp[half ? WP_BWD : WP_FWD], c BP(3));
+      if (half == 0) {
+        WPROF(7);
+        if (lead) tail_solve<M>(G, X, tposT, diag, lane);
+        gsync<WG>(group);
+        WPROF(5);
+      }
     }
   };
 
   for (;;) {
-    int w = 0;
-    if (lane == 0) w = atomicAdd(a.next, 1);
-    w = __shfl_sync(FULLMASK, w, 0);
+    if (gtid == 0) ctl->cell = atomicAdd(a.next, 1);
+    gsync<WG>(group);
+    const int w = ctl->cell;
     if (w >= a.nwork) break;
     const int cell = a.cell_list ? a.cell_list[w] : w;
 
@@ -341,24 +481,25 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
     double Y[NQ], F0[NQ], K1[NQ], K2[NQ], K3[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int e = lane + 32 * q;
+      const int e = gtid + GT * q;
       Y[q] = (e < M::NSPEC) ? a.conc_in[(size_t)e * a.ncell + cell] : 0.0;
       F0[q] = K1[q] = K2[q] = K3[q] = 0.0;
       if (e < M::NSPEC) YG[e] = Y[q];
     }
 #pragma unroll 4
-    for (int r = lane; r < M::NREACT; r += 32) {
+    for (int r = gtid; r < M::NREACT; r += GT) {
       const int i0 = __ldg(awt + r).x & 0xffff;
       __stcg(rcsA + r, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + cell] : P.lit[i0 - M::NREACT]);
     }
 #pragma unroll 4
-    for (int m = lane; m < M::NB; m += 32) {
+    for (int m = gtid; m < M::NB; m += GT) {
       const int i0 = __ldg(bwt + m).x & 0xffff;
       __stcg(rcsB + m, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + cell] : P.lit[i0 - M::NREACT]);
     }
-    __syncwarp();
+    gsync<WG>(group);
 
-    // ---- Rosenbrock() start-up (gckpp_Integrator.F90:420-428, :637)
+    // ---- Rosenbrock() start-up (gckpp_Integrator.F90:420-428, :637); every thread of the group carries the
+    // control state redundantly (identical arithmetic, identical decisions)
     int ist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const double hs = a.hstart ? a.hstart[cell] : o.Hstart_rcntrl;
     const double Hstart = (hs > 0.0) ? fmin(fabs(hs), fabs(o.Tend - o.Tstart)) : fmax(o.Hmin, 1.0E-5);
@@ -378,10 +519,10 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
       if (((T + 0.1 * H) == T) || (H <= o.Roundoff)) { ierr = -7; break; }
       H = fmin(H, fabs(o.Tend - T));
       // Fcn0 = Fun(Y); YG already holds Y (cell load / accepted step)
-      fun(0);
+      fun(WS_VDOT0);
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
-        const int e = lane + 32 * q;
+        const int e = gtid + GT * q;
         F0[q] = (e < N) ? X[e] : 0.0;
       }
       ist[Nfun]++;
@@ -394,29 +535,31 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
         // after a rejected attempt YG holds a stage state: (re)store Y for the Jacobian
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-          const int e = lane + 32 * q;
+          const int e = gtid + GT * q;
           if (e < N) YG[e] = Y[q];
         }
-        // ---- Ghimj = 1/(H*gamma) - Jac0 (:1973-1977); Jac0 is recomputed per attempt
-        for (int k = lane; k < M::NNZ; k += 32) G[k] = 0.0;         // structural zeros / fill-in slots
-        __syncwarp();
-#pragma unroll 2
-        for (int m = lane; m < M::NB; m += 32) {
-          const uint2 w2 = __ldg(bwt + m);
-          const double rc = __ldcg(rcsB + m);
-          SCR[m] = rc * YG[w2.x >> 16] * YG[w2.y & 0xffff] * YG[w2.y >> 16];
-        }
+        // ---- Ghimj = 1/(H*gamma) - Jac0 (:1973-1977); Jac0 is recomputed per attempt, B(m) in two halves
+        for (int k = gtid; k < M::NNZ; k += GT) G[k] = 0.0;         // structural zeros / fill-in slots
+        if (gtid == 0) ctl->sing = 0;
+        gsync<WG>(group);
         c.ghinv = 1.0 / (Dir * H * o.Gamma[0]);
-        c.sing = false;
-        rd.at(P.off_jvs);
-        run_phase<K_JVS>(rd, P.nb[WP_JVS], c);
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+          const int m0 = half * L::NSCR, m1 = cmin(M::NB, m0 + L::NSCR);
+          if (m0 >= m1) break;
+          eval_terms<GT, 9>(bwt, rcsB, YG, SCR, m0, m1, gtid);
+          gsync<WG>(group);
+          rd.at(sof[half ? WS_JVS2 : WS_JVS]);
+          run_phase<K_JVS, WG>(rd, nbp[half ? WP_JVS2 : WP_JVS], c BP(1));
+        }
         WPROF(2);
         // ---- sparse LU (KppDecomp): head pivots from the stream, then the tail block in registers
-        run_phase<K_LU>(rd, P.nb[WP_LU], c);
+        rd.at(sof[WS_LU]);
+        run_phase<K_LU, WG>(rd, nbp[WP_LU], c BP(2));
         WPROF(3);
-        bool sing = tail_lu<M>(G, tposT, lane);
-        sing = __any_sync(FULLMASK, sing || c.sing);
-        __syncwarp();
+        if (lead && tail_lu<M>(G, X, tposT, lane)) ctl->sing = 1;
+        gsync<WG>(group);
+        const bool sing = ctl->sing != 0;
         WPROF(4);
         ist[Ndec]++;
         if (sing) {                                  // ros_PrepareMatrix :1985-1995
@@ -433,18 +576,18 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
           if (st >= 2) {           // the state to evaluate: Y + sum_j A(st,j) K_j
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
-              const int e = lane + 32 * q;
+              const int e = gtid + GT * q;
               if (e < N)
                 YG[e] = (st == 2) ? fma(o.A[2], K2[q], fma(o.A[1], K1[q], Y[q]))
                                   : fma(o.A[5], K3[q], fma(o.A[4], K2[q], fma(o.A[3], K1[q], Y[q])));
             }
-            __syncwarp();
-            fun(st - 1);
+            gsync<WG>(group);
+            fun(st == 2 ? WS_VDOT1 : WS_VDOT2);
           }
           // right-hand side K_st = Fcn + sum_j C(st,j)/H K_j
 #pragma unroll
           for (int q = 0; q < NQ; q++) {
-            const int e = lane + 32 * q;
+            const int e = gtid + GT * q;
             if (e < N) {
               double v;
               if (st == 0) v = F0[q];
@@ -454,13 +597,13 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
               X[e] = v;
             }
           }
-          __syncwarp();
+          gsync<WG>(group);
           WPROF(6);
           solve(st);
           if (st < 3) {
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
-              const int e = lane + 32 * q;
+              const int e = gtid + GT * q;
               const double v = (e < N) ? X[e] : 0.0;
               if (st == 0) K1[q] = v;
               else if (st == 1) K2[q] = v;
@@ -473,7 +616,7 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
         double yn[NQ], e2 = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-          const int e = lane + 32 * q;
+          const int e = gtid + GT * q;
           yn[q] = Y[q];
           if (e < N) {
             const double k4 = X[e];
@@ -487,6 +630,13 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) e2 += __shfl_xor_sync(FULLMASK, e2, off);
+        if (WG > 1) {
+          if (lane == 0) ctl->red[sw] = e2;
+          gsync<WG>(group);
+          e2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < WG; i++) e2 += ctl->red[i];
+        }
         const double Err = fmax(sqrt(e2 / (double)N), 1.0e-10);
         ist[Nfun] += 2; ist[Nsol] += 4;
         const double Fac = fmin(o.FacMax, fmax(o.FacMin, o.FacSafe / pow(Err, 1.0 / o.ELO)));
@@ -496,13 +646,13 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
           ist[Nacc]++;
 #pragma unroll
           for (int q = 0; q < NQ; q++) {
-            const int e = lane + 32 * q;
+            const int e = gtid + GT * q;
             if (e < N) {
               Y[q] = o.ClipNegative ? fmax(yn[q], 0.0) : yn[q];
               YG[e] = Y[q];
             }
           }
-          __syncwarp();
+          gsync<WG>(group);
           T = T + Dir * H;
           Hnew = fmax(o.Hmin, fmin(Hnew, o.Hmax));
           if (rejLast) Hnew = fmin(Hnew, H);
@@ -525,27 +675,31 @@ __global__ void __launch_bounds__(WLay<M>::NWB * 32, 1) ros_warp_kernel(WarpArgs
     // ---- retire the cell
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int e = lane + 32 * q;
+      const int e = gtid + GT * q;
       if (e < M::NSPEC) a.conc_out[(size_t)e * a.ncell + cell] = Y[q];
     }
-    if (a.istatus && lane < 8) {
+    if (a.istatus && gtid < 8) {
       int v = 0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) v = (lane == q) ? ist[q] : v;
-      a.istatus[(size_t)lane * a.ncell + cell] = v;
+      for (int q = 0; q < 8; q++) v = (gtid == q) ? ist[q] : v;
+      a.istatus[(size_t)gtid * a.ncell + cell] = v;
     }
-    if (a.rstatus && lane < 4)
-      a.rstatus[(size_t)lane * a.ncell + cell] = lane == 0 ? Texit : (lane == 1 ? Hexit : (lane == 2 ? Hnewx : 0.0));
-    if (a.ierr && lane == 0) a.ierr[cell] = ierr;
+    if (a.rstatus && gtid < 4)
+      a.rstatus[(size_t)gtid * a.ncell + cell] = gtid == 0 ? Texit : (gtid == 1 ? Hexit : (gtid == 2 ? Hnewx : 0.0));
+    if (a.ierr && gtid == 0) a.ierr[cell] = ierr;
     acc_stp += ist[Nstp]; acc_acc += ist[Nacc]; acc_done++;
     if (ierr < 0) acc_fail++;
     WPROF(9);
   }
 #ifdef WARP_PROFILE
   if (tid == 0 && blockIdx.x == 0 && a.sums)
+  {
     for (int i = 0; i < 12; i++) a.sums[8 + i] = (unsigned long long)pacc_[i];
+    for (int k = 0; k < 4; k++)
+      for (int i = 0; i < 6; i++) a.sums[20 + 6 * k + i] = (unsigned long long)bacc_[k][i];
+  }
 #endif
-  if (lane == 0 && a.sums) {
+  if (gtid == 0 && a.sums) {
     atomicAdd(a.sums + 0, acc_stp);
     atomicAdd(a.sums + 1, acc_acc);
     atomicAdd(a.sums + 2, acc_fail);
@@ -578,12 +732,59 @@ template <class M> static bool dims_match(const gckpp_host_tables_t *T, const gc
          T->nlit == M::NLIT && S->ncoef == M::NCOEF && S->tail == M::TAIL && S->head == M::HEAD;
 }
 
+static int group_warps(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM ? WLay<fullchem_dims>::WG : WLay<Hg_dims>::WG; }
 bool warp_kernel_supports(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM || mech_id == GCKPP_MECH_HG; }
-int warp_cells_per_block(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM ? WLay<fullchem_dims>::NWB : WLay<Hg_dims>::NWB; }
+int warp_cells_per_block(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM ? WLay<fullchem_dims>::NGRP : WLay<Hg_dims>::NGRP; }
 int warp_smem_bytes(int mech_id) { return mech_id == GCKPP_MECH_FULLCHEM ? WLay<fullchem_dims>::TOTAL : WLay<Hg_dims>::TOTAL; }
-size_t warp_rcs_doubles_per_warp(int mech_id)
+size_t warp_rcs_doubles_per_group(int mech_id)
 {
   return mech_id == GCKPP_MECH_FULLCHEM ? (size_t)fullchem_dims::NREACT + fullchem_dims::NB : (size_t)Hg_dims::NREACT + Hg_dims::NB;
+}
+
+// One table phase split into per-warp row sequences: the bundles of a dependency level (wsched.py marks the
+// first bundle of a level with SYNC) are dealt round-robin to the WG warp-streams; in every stream the last
+// bundle of a level gets the SYNC flag (= group barrier after it); a stream without a bundle in a level gets
+// an empty one, so that all warps of a group execute the same number of barriers.
+static void deal_phase(const uint32_t *rows, int nrows, int wg, std::vector<std::vector<uint32_t>> &out, std::vector<int> &nb)
+{
+  out.assign(wg, {});
+  nb.assign(wg, 0);
+  std::vector<std::vector<std::pair<int, int>>> level;          // per stream: (first row, rows) of its bundles in this level
+  auto flush = [&]() {
+    if (level.empty()) return;
+    for (int w = 0; w < wg; w++) {
+      if (level[w].empty()) {                                    // empty bundle: T = 0, nothing written
+        std::vector<uint32_t> row(128, 0u);
+        for (int l = 0; l < 32; l++) row[4 * l + 1] = F_SYNC;
+        out[w].insert(out[w].end(), row.begin(), row.end());
+        nb[w]++;
+        continue;
+      }
+      for (size_t i = 0; i < level[w].size(); i++) {
+        size_t at = out[w].size();
+        out[w].insert(out[w].end(), rows + (size_t)level[w][i].first * 128, rows + (size_t)(level[w][i].first + level[w][i].second) * 128);
+        for (int l = 0; l < 32; l++) {
+          uint32_t &meta = out[w][at + 4 * l + 1];
+          meta &= ~F_SYNC;
+          if (i + 1 == level[w].size()) meta |= F_SYNC;
+        }
+        nb[w]++;
+      }
+    }
+    level.clear();
+  };
+  int r = 0, k = 0;
+  while (r < nrows) {
+    const uint32_t meta = rows[(size_t)r * 128 + 1];
+    const int T = meta & 63;
+    const int n = 1 + (T > 2 ? (T - 2 + 3) / 4 : 0);
+    if (meta & F_SYNC) { flush(); k = 0; }
+    if (level.empty()) level.assign(wg, {});
+    level[k % wg].push_back({r, n});
+    k++;
+    r += n;
+  }
+  flush();
 }
 
 int warp_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_wsched_tables_t *S, WarpHostPlan &hp)
@@ -591,25 +792,30 @@ int warp_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_wsche
   if (!warp_kernel_supports(mech_id)) return -1;
   if (mech_id == GCKPP_MECH_FULLCHEM ? !dims_match<fullchem_dims>(T, S) : !dims_match<Hg_dims>(T, S)) return -2;
   if (T->nspec + T->nlit + 1 >= 65536 || T->nreact + T->nlit >= 65535 || (T->nnz + 1) * 8 >= 65536) return -4;
-  hp.stream.clear();
-  auto push = [&](int ph) {
-    int off = (int)(hp.stream.size() / 128);
-    hp.stream.insert(hp.stream.end(), S->rows[ph], S->rows[ph] + (size_t)S->nrows[ph] * 128);
-    return off;
-  };
+  const int wg = group_warps(mech_id);
+  std::vector<std::vector<uint32_t>> ph[WARP_NPH];
+  std::vector<int> nb[WARP_NPH];
+  for (int p = 0; p < WARP_NPH; p++) deal_phase(S->rows[p], S->nrows[p], wg, ph[p], nb[p]);
   // the order one Rodas3 attempt consumes the tables in (NewF = T,F,T,T)
-  hp.off_vdot[0] = push(WP_VDOT);
-  hp.off_jvs = push(WP_JVS);
-  hp.off_lu = push(WP_LU);
-  hp.off_fwd[0] = push(WP_FWD); hp.off_bwd[0] = push(WP_BWD);
-  hp.off_fwd[1] = push(WP_FWD); hp.off_bwd[1] = push(WP_BWD);
-  hp.off_vdot[1] = push(WP_VDOT);
-  hp.off_fwd[2] = push(WP_FWD); hp.off_bwd[2] = push(WP_BWD);
-  hp.off_vdot[2] = push(WP_VDOT);
-  hp.off_fwd[3] = push(WP_FWD); hp.off_bwd[3] = push(WP_BWD);
-  hp.rows_total = (int)(hp.stream.size() / 128);
-  if (hp.rows_total < 2 * RS) return -5;
-  for (int p = 0; p < 5; p++) hp.nb[p] = S->nbundles[p];
+  static const int seg_phase[WARP_NSEG] = {WP_VDOT, WP_JVS, WP_JVS2, WP_LU, WP_FWD, WP_BWD, WP_FWD, WP_BWD, WP_VDOT, WP_FWD, WP_BWD,
+                                           WP_VDOT, WP_FWD, WP_BWD};
+  hp.stream.clear();
+  for (int w = 0; w < WARP_WG; w++) { hp.w_off[w] = 0; hp.w_rows[w] = 0; }
+  for (int w = 0; w < wg; w++) {
+    hp.w_off[w] = (int)(hp.stream.size() / 128);
+    std::vector<uint32_t> ws;
+    for (int sg = 0; sg < WARP_NSEG; sg++) {
+      hp.seg_off[w][sg] = (int)(ws.size() / 128);
+      ws.insert(ws.end(), ph[seg_phase[sg]][w].begin(), ph[seg_phase[sg]][w].end());
+    }
+    // a segment that ends the stream wraps to row 0
+    const int rows = (int)(ws.size() / 128);
+    for (int sg = 0; sg < WARP_NSEG; sg++) if (hp.seg_off[w][sg] >= rows) hp.seg_off[w][sg] = 0;
+    if (rows < 2 * RS) return -5;
+    hp.w_rows[w] = rows;
+    hp.stream.insert(hp.stream.end(), ws.begin(), ws.end());
+    for (int p = 0; p < WARP_NPH; p++) hp.nb[w][p] = nb[p][w];
+  }
   hp.aw.resize(2 * (size_t)T->nreact);
   for (int r = 0; r < T->nreact; r++) encode_term(T->a_term + 4 * r, T->nreact, T->nspec, T->nlit, &hp.aw[2 * r]);
   hp.bw.resize(2 * (size_t)(T->nb > 0 ? T->nb : 1));
@@ -626,7 +832,7 @@ static cudaError_t launch_t(const WarpArgs &P, const RosArgs &a, int blocks, cud
   // the opt-in is a per-device attribute of the function: set it on every launch (cheap) rather than cache it per process
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, WLay<M>::TOTAL);
   if (e != cudaSuccess) return e;
-  k<<<blocks, WLay<M>::NWB * 32, WLay<M>::TOTAL, s>>>(P, a);
+  k<<<blocks, WLay<M>::NGRP * WLay<M>::GT, WLay<M>::TOTAL, s>>>(P, a);
   return cudaGetLastError();
 }
 

@@ -66,6 +66,7 @@ def load_library(path=None):
     L.gckpp_gpu_last_error.restype = C.c_char_p
     L.gckpp_gpu_plan_info.argtypes = [C.c_int, ip]
     L.gckpp_gpu_set_keep_active.argtypes = [vp, C.c_int, ip]
+    L.gckpp_gpu_warp_plan.argtypes = [C.c_int, ip, C.c_int, vp, C.c_int64]
     _lib = L
     return L
 
@@ -74,7 +75,7 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
            "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
            "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error", "gckpp_gpu_set_stream",
-           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active"]
+           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active", "gckpp_gpu_warp_plan"]
 
 
 def plan_info(mech):
@@ -85,6 +86,23 @@ def plan_info(mech):
         raise KppError(L.gckpp_gpu_last_error().decode())
     return dict(zip(("smem_bytes", "stream_rows", "resident_rows", "rounds", "n_lu", "n_fwd", "n_bwd", "cells_per_block"),
                     (int(x) for x in d)))
+
+
+def warp_plan(mech):
+    """per-warp table streams of the warp-group kernel as the host plan lays them out (host-only query)"""
+    L = load_library()
+    info = (C.c_int32 * 256)()
+    if L.gckpp_gpu_warp_plan(MECH_ID[mech], info, 256, None, 0) != 0:
+        raise KppError(L.gckpp_gpu_last_error().decode())
+    wg, cpb, smem, rows, nseg, nph, rs, per = (int(x) for x in info[:8])
+    stream = np.zeros((rows, 32, 4), np.uint32)
+    if L.gckpp_gpu_warp_plan(MECH_ID[mech], info, 256, stream.ctypes.data_as(C.c_void_p), stream.size) != 0:
+        raise KppError(L.gckpp_gpu_last_error().decode())
+    warps = []
+    for w in range(wg):
+        o = [int(x) for x in info[8 + w * per: 8 + (w + 1) * per]]
+        warps.append(dict(off=o[0], rows=o[1], seg_off=o[2:2 + nseg], nb=o[2 + nseg:2 + nseg + nph]))
+    return dict(wg=wg, cells_per_block=cpb, smem_bytes=smem, ring_slots=rs, stream=stream, warps=warps)
 
 
 def mech_dims(mech):

@@ -13,7 +13,8 @@ dependency level at which all of its operands are final.  A bundle whose operand
 an earlier bundle of the same phase carries a SYNC flag (= start of a dependency level).
 
   vdot  X(i)  = sum coef * A(r)                                    (aggregate form of Fun)
-  jvs   G(k)  = [1/(H*gamma) on the diagonal] - sum coef * B(m)
+  jvs   G(k)  = G(k) [+ 1/(H*gamma) on the diagonal] - sum coef * B(m)      (G cleared first; the scratch holds
+        NREACT doubles, so B(m) is evaluated in two halves: "jvs" uses B(0..NREACT-1), "jvs2" the rest)
   lu    head pivots j < h only (the last m = min(32, NVAR) rows/columns form the TAIL, factorised by
         the kernel in registers):
           L entry (k,c), c < k, c < h :  G = (G - sum_j L(k,j) U(j,c)) * rinv(c)
@@ -48,7 +49,7 @@ TAIL = 32
 NONE = 0xFFFF
 
 F_SYNC, F_WRITE, F_MUL, F_DIAG = 1 << 9, 1 << 10, 1 << 11, 1 << 12
-PHASES = ["vdot", "jvs", "lu", "fwd", "bwd"]
+PHASES = ["vdot", "jvs", "jvs2", "lu", "fwd", "bwd"]
 
 
 def _pow2ceil(x):
@@ -176,6 +177,64 @@ def bundle_rows(b):
     return out
 
 
+def split_bundles(rows):
+    """[(first row, number of rows, meta of lane 0)] of the bundles in a row array"""
+    out = []
+    r = 0
+    while r < rows.shape[0]:
+        meta = int(rows[r, 0, 1])
+        T = meta & 63
+        n = 1 + (max(T - 2, 0) + 3) // 4
+        out.append((r, n, meta))
+        r += n
+    return out
+
+
+def run_rows(rows, hi_arr, lo_arr, tgt_arr, mode, ghinv=0.0):
+    """numpy emulation of the kernel's bundle engine on a row array -> (singular flag, bundles executed)"""
+    sing = False
+    nb = 0
+    for r, nrows, _ in split_bundles(rows):
+        row0 = rows[r]
+        hdr = row0[:, 0].astype(np.int64)
+        meta = row0[:, 1].astype(np.int64)
+        T = int(meta[0] & 63)
+        lg = int((meta[0] >> 6) & 7)
+        assert np.all((meta & 63) == T) and np.all(((meta >> 6) & 7) == lg)
+        assert np.all((meta & F_SYNC) == (meta[0] & F_SYNC))
+        words = rows[r:r + nrows].transpose(1, 0, 2).reshape(32, -1)[:, 2:2 + T].astype(np.int64)
+        nb += 1
+        a = [np.zeros(32) for _ in range(4)]
+        for k in range(T):
+            w = words[:, k]
+            a[k & 3] = a[k & 3] + hi_arr[(w >> 16) >> 3] * lo_arr[(w & 0xffff) >> 3]
+        acc = (a[0] + a[1]) + (a[2] + a[3])
+        for s in range(lg):
+            sh = np.zeros(32)
+            sh[:32 - (1 << s)] = acc[(1 << s):]
+            acc = acc + sh
+        tg = (hdr & 0xffff) >> 3
+        ax = (hdr >> 16) >> 3
+        for l in range(32):
+            if not (meta[l] & F_WRITE):
+                continue
+            if mode == "vdot":
+                tgt_arr[tg[l]] = acc[l]
+            elif mode == "jvs":
+                tgt_arr[tg[l]] = (tgt_arr[tg[l]] - acc[l]) + (ghinv if (meta[l] & F_DIAG) else 0.0)
+            else:
+                v = tgt_arr[tg[l]] - acc[l]
+                if meta[l] & F_MUL:
+                    v = v * hi_arr[ax[l]]
+                if meta[l] & F_DIAG:
+                    if not (abs(v) >= np.finfo(np.float64).tiny):
+                        sing = True
+                    with np.errstate(divide="ignore"):
+                        v = 1.0 / v
+                tgt_arr[tg[l]] = v
+    return sing, nb
+
+
 class WSchedule:
     def __init__(self, mech, lmax=LMAX, tail=TAIL, optimise=True):
         self.mech = mech
@@ -222,14 +281,25 @@ class WSchedule:
 
         vd = [(i * 8, 0, 0, coef_terms(mech.Vdot[i], "A")) for i in range(n)]
         dset = set(diag)
-        jv = [(k * 8, 0, F_DIAG if k in dset else 0, coef_terms(mech.JVS[k], "B")) for k in range(nnz)
-              if mech.JVS[k] or k in dset]
+        # B(m) is evaluated in two halves through a scratch of NREACT doubles: a target's terms are split by half
+        self.nscr = mech.nreact
+        assert len(mech.B) <= 2 * self.nscr
+        jv, jv2 = [], []
+        for k in range(nnz):
+            terms = coef_terms(mech.JVS[k], "B")
+            t1 = [(c, b) for c, b in terms if b < self.nscr * 8]
+            t2 = [(c, b - self.nscr * 8) for c, b in terms if b >= self.nscr * 8]
+            if t1 or k in dset:
+                jv.append((k * 8, 0, F_DIAG if k in dset else 0, t1))
+            if t2:
+                jv2.append((k * 8, 0, 0, t2))
         ncoef = len(self.coefs)
         self.coefs.append(0.0)                      # slot ncoef holds 0.0: padding terms of vdot / jvs
         self.coefs = np.array(self.coefs, np.float64)
         PAD_SUM = (ncoef * 8, 0)
         PAD_G = (nnz * 8, nnz * 8)                  # G slot NNZ holds 0.0
-        PAD_SOLVE = (nnz * 8, 0)
+        self.xpad = max(n, 64)                      # X slot XPAD holds 0.0 and is never written (X[0..63] doubles as a buffer)
+        PAD_SOLVE = (nnz * 8, self.xpad * 8)
         self.phase = {}
 
         P = Packer(PAD_SUM, lmax, optimise)
@@ -238,6 +308,10 @@ class WSchedule:
         P = Packer(PAD_SUM, lmax, optimise)
         P.add_level(jv)
         self.phase["jvs"] = P.bundles
+        P = Packer(PAD_SUM, lmax, optimise)
+        if jv2:
+            P.add_level(jv2)
+        self.phase["jvs2"] = P.bundles
 
         # ---- LU, head pivots, pull form ----
         lev = {}
@@ -340,48 +414,7 @@ class WSchedule:
     def run_phase(self, name, hi_arr, lo_arr, tgt_arr, mode, ghinv=0.0):
         """hi_arr/lo_arr/tgt_arr: float64 arrays indexed by byte offset / 8.  mode in vdot, jvs, lu, solve.
         Returns True if a (near-)zero pivot was met (lu)."""
-        rows = self.phase_rows(name)
-        r = 0
-        sing = False
-        nb = 0
-        while r < rows.shape[0]:
-            row0 = rows[r]
-            hdr = row0[:, 0].astype(np.int64)
-            meta = row0[:, 1].astype(np.int64)
-            T = int(meta[0] & 63)
-            lg = int((meta[0] >> 6) & 7)
-            assert np.all((meta & 63) == T) and np.all(((meta >> 6) & 7) == lg)
-            nrows = 1 + (max(T - 2, 0) + 3) // 4
-            words = rows[r:r + nrows].transpose(1, 0, 2).reshape(32, -1)[:, 2:2 + T].astype(np.int64)
-            r += nrows
-            nb += 1
-            a = [np.zeros(32), np.zeros(32)]
-            for k in range(T):
-                w = words[:, k]
-                a[k & 1] = a[k & 1] + hi_arr[(w >> 16) >> 3] * lo_arr[(w & 0xffff) >> 3]
-            acc = a[0] + a[1]
-            for s in range(lg):
-                sh = np.zeros(32)
-                sh[:32 - (1 << s)] = acc[(1 << s):]
-                acc = acc + sh
-            tg = (hdr & 0xffff) >> 3
-            ax = (hdr >> 16) >> 3
-            for l in range(32):
-                if not (meta[l] & F_WRITE):
-                    continue
-                if mode == "vdot":
-                    tgt_arr[tg[l]] = acc[l]
-                elif mode == "jvs":
-                    tgt_arr[tg[l]] = (ghinv if (meta[l] & F_DIAG) else 0.0) - acc[l]
-                else:
-                    v = tgt_arr[tg[l]] - acc[l]
-                    if meta[l] & F_MUL:
-                        v = v * hi_arr[ax[l]]
-                    if meta[l] & F_DIAG:
-                        if not (abs(v) >= np.finfo(np.float64).tiny):
-                            sing = True
-                        v = 1.0 / v
-                    tgt_arr[tg[l]] = v
+        sing, nb = run_rows(self.phase_rows(name), hi_arr, lo_arr, tgt_arr, mode, ghinv)
         assert nb == len(self.phase[name])
         return sing
 
@@ -392,7 +425,9 @@ class WSchedule:
 
     def emulate_jac(self, B, ghinv):
         G = np.zeros(self.nnz + 1)
-        self.run_phase("jvs", self.coefs, B, G, "jvs", ghinv)
+        B = np.concatenate([B, np.zeros(2 * self.nscr - len(B))])
+        self.run_phase("jvs", self.coefs, B[:self.nscr], G, "jvs", ghinv)
+        self.run_phase("jvs2", self.coefs, B[self.nscr:], G, "jvs", ghinv)
         return G
 
     def _tail_dense(self, G):
@@ -429,19 +464,27 @@ class WSchedule:
                     assert D[i, j] == 0.0
         return G, sing
 
-    def emulate_solve(self, G, X):
-        m, h = self.m, self.h
+    def xbuf(self, x):
+        """right-hand side in the kernel's X array: slot XPAD holds the 0.0 padding terms read"""
+        X = np.zeros(self.xpad + 1)
+        X[:self.n] = x
+        return X
+
+    def emulate_solve(self, G, x):
+        m, h, n = self.m, self.h, self.n
+        X = self.xbuf(x)
         self.run_phase("fwd", G, X, X, "solve")
         D = self._tail_dense(G)
-        x = X[h:].copy()
+        t = X[h:n].copy()
         for j in range(m - 1):
-            x = x - np.where(np.arange(m) > j, D[:, j], 0.0) * x[j]
-        x = x * np.diag(D)
+            t = t - np.where(np.arange(m) > j, D[:, j], 0.0) * t[j]
+        t = t * np.diag(D)
         for j in range(m - 1, 0, -1):
-            x = x - np.where(np.arange(m) < j, D[:, j], 0.0) * x[j]
-        X[h:] = x
+            t = t - np.where(np.arange(m) < j, D[:, j], 0.0) * t[j]
+        X[h:n] = t
         self.run_phase("bwd", G, X, X, "solve")
-        return X
+        assert X[self.xpad] == 0.0
+        return X[:n]
 
 
 if __name__ == "__main__":

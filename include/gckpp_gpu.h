@@ -163,6 +163,9 @@ int gckpp_gpu_set_keep_active(gckpp_gpu_handle_t *handle, int n, const int32_t *
  * info[2] resident table rows, info[3] rounds in the directory, info[4..6] LU / forward / backward
  * rounds, info[7] cells per block. */
 int gckpp_gpu_plan_info(int mech_id, int32_t *info /* [8] */);
+/* Test hook: the per-warp table streams of the warp-group integrator (csrc/ros_warp.h) exactly as the host plan
+ * lays them out, so that CPU tests can replay them (tests/test_wsched.py).  No reference counterpart. */
+int gckpp_gpu_warp_plan(int mech_id, int32_t *info, int info_cap, uint32_t *stream_out, int64_t stream_cap_words);
 
 /* Last error text (thread-local). */
 const char *gckpp_gpu_last_error(void);

@@ -64,29 +64,107 @@ def test_wschedule_structure():
     s = wsched.WSchedule(m)
     for name in ("lu", "fwd", "bwd"):
         seen = set()
-        level_writes = set()
+        levels = []
         for b in s.phase[name]:
             if b.sync:
-                level_writes = set()
-            reads = set()
+                levels.append((set(), set()))
+            reads, writes = levels[-1]
             for l in range(32):
                 if b.flags[l] & wsched.F_WRITE:
                     t = b.hdr[l] & 0xffff
                     assert t not in seen
                     seen.add(t)
+                    writes.add(t)
                 for hi, lo in b.terms[l]:
                     reads.add(("G", hi))
                     reads.add(("G" if name == "lu" else "X", lo))
                 if b.flags[l] & wsched.F_MUL:
                     reads.add(("G", b.hdr[l] >> 16))
-            tk = "G" if name == "lu" else "X"
-            assert not (reads & {(tk, t) for t in level_writes})
-            for l in range(32):
-                if b.flags[l] & wsched.F_WRITE:
-                    level_writes.add(b.hdr[l] & 0xffff)
+        tk = "G" if name == "lu" else "X"
+        for reads, writes in levels:          # the bundles of a level run concurrently on the warps of a group
+            assert not (reads & {(tk, t) for t in writes})
     # singular matrix is flagged
     G = np.zeros(s.nnz + 1)
     G[np.array(m.lu_diag)] = 1.0
     G[m.lu_diag[5]] = 0.0
     _, sing = s.emulate_lu(G)
     assert sing
+
+
+@pytest.mark.parametrize("mech", ["fullchem", "Hg"])
+def test_host_plan_replay(mech, lib):
+    """The per-warp streams the C++ host plan builds (bundles of a dependency level dealt over the warps of a group,
+    group barrier after a warp's last bundle of a level) replayed level by level must give what the single
+    stream gives: same LU factors and solution, and every warp-stream must hold the same number of barriers."""
+    from geos_chem_b200 import kpp
+    m = ir.load(mech)
+    s = wsched.WSchedule(m)
+    plan = kpp.warp_plan(mech)
+    wg = plan["wg"]
+    assert wg == (4 if mech == "fullchem" else 1)
+    SEG = ["vdot", "jvs", "jvs2", "lu", "fwd", "bwd", "fwd", "bwd", "vdot", "fwd", "bwd", "vdot", "fwd", "bwd"]
+    PH = wsched.PHASES
+
+    def seg_levels(w, seg):
+        """row chunks of warp-stream w for segment seg, one chunk per dependency level"""
+        W = plan["warps"][w]
+        rows = plan["stream"][W["off"]:W["off"] + W["rows"]]
+        nb = W["nb"][PH.index(SEG[seg])]
+        r = W["seg_off"][seg]
+        out, cur = [], []
+        for _ in range(nb):
+            meta = int(rows[r, 0, 1]); T = meta & 63
+            n = 1 + (max(T - 2, 0) + 3) // 4
+            cur.append(rows[r:r + n])
+            r += n
+            if meta & wsched.F_SYNC:
+                out.append(np.concatenate(cur)); cur = []
+        assert not cur, "a warp-stream must end every level with a barrier"
+        # segments follow each other in the cyclic stream
+        nxt = W["seg_off"][(seg + 1) % len(SEG)]
+        assert r % W["rows"] == nxt
+        return out
+
+    def replay(seg, hi, lo, tgt, mode, ghinv=0.0):
+        lv = [seg_levels(w, seg) for w in range(wg)]
+        assert len({len(x) for x in lv}) == 1, "all warps of a group execute the same number of barriers"
+        sing = False
+        for i in range(len(lv[0])):
+            for w in reversed(range(wg)):          # any order within a level
+                sg, _ = wsched.run_rows(lv[w][i], hi, lo, tgt, mode, ghinv)
+                sing |= sg
+        return sing
+
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal(m.nreact)
+    X = np.zeros(m.nvar)
+    replay(0, s.coefs, A, X, "vdot")
+    np.testing.assert_array_equal(X, s.emulate_fun(A))
+    X2 = np.zeros(m.nvar)
+    replay(8, s.coefs, A, X2, "vdot")
+    np.testing.assert_array_equal(X2, X)
+    B = rng.standard_normal(len(m.B))
+    Bp = np.concatenate([B, np.zeros(2 * s.nscr - len(B))])
+    G = np.zeros(s.nnz + 1)
+    replay(1, s.coefs, Bp[:s.nscr], G, "jvs", 0.25)
+    replay(2, s.coefs, Bp[s.nscr:], G, "jvs", 0.25)
+    np.testing.assert_array_equal(G, s.emulate_jac(B, 0.25))
+    # a diagonally dominant matrix on the pattern
+    G = np.append(rng.standard_normal(s.nnz) * 0.1, 0.0)
+    G[np.array(m.lu_diag)] = 3.0 + rng.uniform(size=m.nvar)
+    Gref, _ = s.emulate_lu(G.copy())
+    Gw = G.copy()
+    assert not replay(3, Gw, Gw, Gw, "lu")
+    # the head phase only: compare entries outside the tail block (the tail LU is the kernel's register code)
+    tail = set(int(p) for p in s.tposT.reshape(-1) if p != wsched.NONE)
+    head = np.array([k for k in range(s.nnz) if k not in tail], dtype=np.int64)
+    if head.size:
+        np.testing.assert_array_equal(Gw[head], Gref[head])
+    for seg in (4, 6, 9, 12):
+        b = rng.standard_normal(m.nvar)
+        xr = s.xbuf(b); wsched.run_rows(s.phase_rows("fwd"), Gref, xr, xr, "solve")
+        xw = s.xbuf(b); replay(seg, Gref, xw, xw, "solve")
+        np.testing.assert_array_equal(xw, xr)
+        xr = s.xbuf(b); wsched.run_rows(s.phase_rows("bwd"), Gref, xr, xr, "solve")
+        xw = s.xbuf(b); replay(seg + 1, Gref, xw, xw, "solve")
+        np.testing.assert_array_equal(xw, xr)
