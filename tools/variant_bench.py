@@ -1,5 +1,5 @@
 """time the integrator on the full 4x5 grid (device-resident inputs) under a few launch conditions"""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, ".")
 import torch
@@ -21,7 +21,7 @@ kw = {}
 if "prealloc" in mode:
     kw = dict(C_out=torch.empty_like(conc), ISTATUS=torch.empty((8, n), dtype=torch.int32, device=dev),
               RSTATUS=torch.empty((4, n), dtype=torch.float64, device=dev), IERR=torch.empty((n,), dtype=torch.int32, device=dev))
-for it in range(4):
+for it in range(int(os.environ.get("VB_ITERS", "4"))):
     out = s.Integrate(0.0, 1200.0, conc, None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs, TEMP=temp, NUMDEN=numden, H2O=h2o, PHOTOL=photol, khet=khet, **kw)
     st = s.last_stats()
     print(mode, it, "integrate %.1f ms" % st["integrate_ms"], "cells/s %.0f" % (n / st["integrate_ms"] * 1e3), flush=True)
