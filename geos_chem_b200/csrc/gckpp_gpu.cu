@@ -500,6 +500,7 @@ static int prepare_warp(gckpp_gpu_handle *h)
     for (int i = 0; i < WARP_NSEG; i++) A.seg_off[w][i] = p.seg_off[w][i];
     for (int i = 0; i < WARP_NPH; i++) A.nb[w][i] = p.nb[w][i];
   }
+  for (int i = 0; i < WARP_NPH; i++) A.nlev[i] = p.nlev[i];
   A.tpos = h->w_tpos.as<uint16_t>(); A.diag = h->w_diag.as<uint16_t>();
   A.aw = h->w_aw.as<uint32_t>(); A.bw = h->w_bw.as<uint32_t>();
   A.coefs = h->w_coefs.as<double>(); A.lit = h->M.lit;
@@ -1005,7 +1006,7 @@ extern "C" int gckpp_gpu_plan_info(int mech_id, int32_t *info)
 
 // Test hook: the per-warp table streams of the warp-group kernel as the host plan lays them out.
 //   info[0] = warps per group, info[1] = cells per block, info[2] = shared memory bytes, info[3] = total rows;
-//   then per warp-stream w (8 + WARP_NSEG + WARP_NPH ints each, starting at info[8]): w_off, w_rows, seg_off[], nb[].
+//   info[8..8+NPH) = levels per phase; then per warp-stream w (2 + WARP_NSEG + WARP_NPH ints each): w_off, w_rows, seg_off[], nb[].
 extern "C" int gckpp_gpu_warp_plan(int mech_id, int32_t *info, int info_cap, uint32_t *stream_out, int64_t stream_cap_words)
 {
   const gckpp_host_tables_t *T = host_tables(mech_id);
@@ -1015,13 +1016,14 @@ extern "C" int gckpp_gpu_warp_plan(int mech_id, int32_t *info, int info_cap, uin
   int rc = warp_plan_build(mech_id, T, S, p);
   if (rc) return fail(-11, "plan failed (%d)", rc);
   const int per = 2 + WARP_NSEG + WARP_NPH;
-  if (info_cap < 8 + WARP_WG * per) return fail(-10, "info too small");
+  if (info_cap < 8 + WARP_NPH + WARP_WG * per) return fail(-10, "info too small");
   int wg = 0;
   for (int w = 0; w < WARP_WG; w++) if (p.w_rows[w] > 0) wg = w + 1;
   info[0] = wg; info[1] = warp_cells_per_block(mech_id); info[2] = warp_smem_bytes(mech_id); info[3] = (int)(p.stream.size() / 128);
   info[4] = WARP_NSEG; info[5] = WARP_NPH; info[6] = WARP_RS; info[7] = per;
+  for (int i = 0; i < WARP_NPH; i++) info[8 + i] = p.nlev[i];
   for (int w = 0; w < wg; w++) {
-    int32_t *o = info + 8 + w * per;
+    int32_t *o = info + 8 + WARP_NPH + w * per;
     o[0] = p.w_off[w]; o[1] = p.w_rows[w];
     for (int i = 0; i < WARP_NSEG; i++) o[2 + i] = p.seg_off[w][i];
     for (int i = 0; i < WARP_NPH; i++) o[2 + WARP_NSEG + i] = p.nb[w][i];

@@ -64,7 +64,8 @@ namespace {
 
 constexpr int RS = WARP_RS;
 constexpr unsigned TNONE = 0xFFFFu;
-constexpr unsigned F_SYNC = 1u << 9, F_WRITE = 1u << 10, F_MUL = 1u << 11, F_DIAG = 1u << 12;
+constexpr unsigned F_SYNC = 1u << 9, F_WRITE = 1u << 10, F_MUL = 1u << 11, F_DIAG = 1u << 12, F_UDIAG = 1u << 18;
+constexpr int PRE_SHIFT = 13, PRE_MAX = 31;      // meta bits 13-17: group barriers of levels without a bundle of this warp, executed before the bundle
 constexpr int SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per block on sm_100
 
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -93,11 +94,11 @@ struct WLay {
   static constexpr int oGRP = a128(oDIAG + M::NVAR * 2);
   // one group's slice (every array 128-byte aligned: the bank analysis of wsched.py is relative to that)
   static constexpr int gG = 0;
-  static constexpr int gYG = a128((M::NNZ + 1) * 8);
+  static constexpr int gYG = a128((M::NNZ + 2) * 8);          // G[NNZ] = 0.0, G[NNZ+1] = 1.0
   static constexpr int gX = gYG + a128(NYG * 8);
   static constexpr int XPAD = cmax(M::NVAR, 64);           // X[XPAD] = 0.0, the operand of padding terms (never written)
   static constexpr int gSCR = gX + a128((XPAD + 1) * 8);   // X[0..63] doubles as the pivot-row buffer of tail_lu
-  static constexpr int gCTL = gSCR + a128(NSCR * 8);
+  static constexpr int gCTL = gSCR + a128(cmax(NSCR * 8, 16 * 32 * 8));   // SCR doubles as the L panel of tail_lu
   static constexpr int gRING = gCTL + a128((int)sizeof(GCtl));
   static constexpr int GSZ = gRING + WG * RS * 512;
   static constexpr int NGRP = cmin(cmin(1024 / GT, WG == 1 ? 16 : 15), (SMEM_LIMIT - oGRP) / GSZ);
@@ -115,36 +116,40 @@ __device__ __forceinline__ void gsync(int group)
 }
 
 // ---- streamed tables: 16 bytes per lane per row, cp.async ring ----------------------------------------
+// The stream of a warp holds the rows of one attempt TWICE (+ RS rows), so the prefetch never has to wrap inside
+// an attempt: `pos` is folded back by L at the start of a phase only.  Slot k of the ring is refilled right after
+// it has been read (the copy lands hundreds of cycles after the read has executed).
 struct WReader {
   const uint4 *gsrc;        // this lane's column of the warp's stream
   uint32_t ring;            // shared-space byte address of this lane's column of the warp's ring
-  int L, irow, islot, cslot, pos;
-  __device__ __forceinline__ void issue()
-  {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
-                 :: "r"(ring + islot * 512), "l"(gsrc + (size_t)irow * 32) : "memory");
-    if (++irow == L) irow = 0;
-    if (++islot == RS) islot = 0;
-  }
+  int L, pos, slot;         // rows of one attempt, next row to consume, its ring slot
   __device__ __forceinline__ void seek(int row)
   {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    pos = irow = row; islot = 0; cslot = 0;
-#pragma unroll 1
-    for (int i = 0; i < RS - 1; i++) issue();
+    pos = row; slot = 0;
+#pragma unroll
+    for (int i = 0; i < RS; i++)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                   :: "r"(ring + i * 512), "l"(gsrc + (size_t)(row + i) * 32) : "memory");
   }
   // the stream is consumed in the fixed order of an accepted attempt; anything else (rejected step,
   // singular matrix, failed cell) re-positions the ring
-  __device__ __forceinline__ void at(int row) { if (pos != row) seek(row); }
+  __device__ __forceinline__ void at(int row)
+  {
+    if (pos >= L) pos -= L;
+    if (pos != row) seek(row);
+  }
   __device__ __forceinline__ uint4 next()
   {
     uint4 v;
-    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 2) : "memory");
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + cslot * 512) : "memory");
-    if (++cslot == RS) cslot = 0;
-    if (++pos == L) pos = 0;
-    issue();
+    const uint32_t sa = ring + slot * 512;
+    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 1) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
+                 :: "r"(sa), "l"(gsrc + (size_t)(pos + RS) * 32) : "memory");
+    pos++;
+    if (++slot == RS) slot = 0;
     return v;
   }
 };
@@ -181,11 +186,12 @@ __device__ __forceinline__ double rcp_fast(double x)
 // lane that owns the target finishes it; a bundle that ends a dependency level is followed by the group barrier.
 template <int KIND, int WG>
 #ifdef WARP_PROFILE
-__device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c, long long *bp = nullptr)
+__device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c, long long *bp = nullptr)
 #else
-__device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c)
+__device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c)
 #endif
 {
+  int done = 0;          // group barriers executed in this phase; every warp of the group executes nlev of them
 #ifdef WARP_PROFILE
   unsigned bsink_ = 0;
   long long bt_;
@@ -201,11 +207,12 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c)
     const int T = meta & 63, lg = (meta >> 6) & 7;
     const bool wr = (meta & F_WRITE) != 0;
     BSINK32(meta); BPROF(0);
+    for (int i = (meta >> PRE_SHIFT) & PRE_MAX; i > 0; i--) { gsync<WG>(c.group); done++; }
+    BPROF(4);
+    // target and scale are loaded by every lane (lanes that write nothing point at the 0.0 / 1.0 slots)
     double old = 0.0, mul = 1.0;
-    if (KIND != K_VDOT) {
-      if (wr) old = ldb(Tb, hdr & 0xffffu);
-      if (KIND != K_JVS && wr && (meta & F_MUL)) mul = ldb(c.Gb, hdr >> 16);
-    }
+    if (KIND != K_VDOT) old = ldb(Tb, hdr & 0xffffu);
+    if (KIND == K_LU || KIND == K_SOLVE) mul = ldb(c.Gb, hdr >> 16);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #define LDT(w, hv, lv) const double hv = ldb(Hb, (w) >> 16), lv = ldb(Lb, (w) & 0xffffu)
 #define LDP(p, w, hv, lv) double hv = 0.0, lv = 0.0; if (p) { hv = ldb(Hb, (w) >> 16); lv = ldb(Lb, (w) & 0xffffu); }
@@ -241,82 +248,125 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, WCtx &c)
     BSINKD(acc); BPROF(1);
     for (int s = 0; s < lg; s++) acc += __shfl_down_sync(FULLMASK, acc, 1 << s);
     BSINKD(acc); BPROF(2);
-    if (wr) {
+    {
       const unsigned t = hdr & 0xffffu;
-      if (KIND == K_VDOT) {
-        stb(Tb, t, acc);
-      } else if (KIND == K_JVS) {
-        stb(Tb, t, (old - acc) + ((meta & F_DIAG) ? c.ghinv : 0.0));
-      } else {
-        double v = (old - acc) * mul;
-        if (KIND == K_LU && (meta & F_DIAG)) {
+      double v;
+      if (KIND == K_VDOT) v = acc;
+      else if (KIND == K_JVS) v = (old - acc) + ((meta & F_DIAG) ? c.ghinv : 0.0);
+      else v = (old - acc) * mul;
+      if (KIND == K_LU && (meta & F_UDIAG)) {              // uniform: some lane of the bundle finishes a pivot
+        if (meta & F_DIAG) {
           if (!(fabs(v) >= DBL_MIN)) c.ctl->sing = 1;      // singular test of ros_PrepareMatrix, also catches NaN
           v = rcp_fast(v);
         }
-        stb(Tb, t, v);
       }
+      if (wr) stb(Tb, t, v);
     }
     BPROF(3);
-    if (meta & F_SYNC) gsync<WG>(c.group);
+    if (meta & F_SYNC) { gsync<WG>(c.group); done++; }
     BPROF(4);
   }
+  for (; done < nlev; done++) gsync<WG>(c.group);
 #ifdef WARP_PROFILE
   if (bp) { bp[5] += nb; if (bsink_ == 0x12345678u) bp[5]++; }
 #endif
 }
 
 // ---- tail block ------------------------------------------------------------------------------------------
-// Dense right-looking LU of the Schur complement by ONE warp: lane i holds row i in registers r[0..m-1].  The pivot
-// loop is fully unrolled (static register indices, no rotation); the pivot row is published by its owner lane
-// through a double-buffered shared-memory row and read back as broadcasts; the reciprocal of the NEXT pivot is
-// started as soon as its entry has been updated, so it overlaps the rest of the row update.  Entries outside the
-// LU pattern are exact zeros and stay zero (fill-in closure).  The factors are stored in their final form:
-// L multipliers, the reciprocal diagonal, and U entries scaled by the reciprocal diagonal of their row.
+// Dense right-looking LU of the m x m Schur complement (m = 32) by ONE warp, lane i = row i, in two column panels
+// of 16 so that a lane holds 16 doubles, not 32:
+//   A  factor the 32 x 16 panel of columns 0..15 (pivots 0..15); the multipliers go to a dense L panel in shared memory
+//   B  apply those 16 pivots to columns 16..31 (row j of U is published by lane j, multipliers come from the L panel)
+//   C  factor the trailing 16 x 16 block (pivots 16..31, lanes 16..31)
+// Pivot loops are fully unrolled (static register indices); a pivot row is published by its owner lane through a
+// double-buffered shared-memory row and read back as broadcasts; the reciprocal of the NEXT pivot is started as soon
+// as its entry has been updated.  Entries outside the LU pattern are exact zeros and stay zero (fill-in closure).
+// The factors are stored in their final form: L multipliers, the reciprocal diagonal, and U entries scaled by the
+// reciprocal diagonal of their row.
 template <class M>
-__device__ __forceinline__ bool tail_lu(double *Gc, double *buf, const uint16_t *tposT, int lane)
+__device__ __forceinline__ bool tail_lu(double *Gc, double *buf /* 2 x 16 */, double *lpan /* 16 x 32 */, const uint16_t *tposT, int lane)
 {
-  constexpr int m = M::TAIL;
-  static_assert(m % 2 == 0, "pairs of columns");
-  double r[m];
-#pragma unroll
-  for (int k = 0; k < m; k++) {
-    const unsigned p = tposT[k * 32 + lane];
-    r[k] = (p != TNONE) ? Gc[p] : 0.0;
-  }
-  double rinv = rcp_fast(__shfl_sync(FULLMASK, r[0], 0));
+  constexpr int m = M::TAIL, hp = 16;
+  static_assert(m == 2 * hp, "two panels of 16 columns");
   double myrd = 0.0;
   bool sing = false;
+  // one panel factorisation: pivots j0..j0+15 on the 16 columns held in r[]
+  auto factor = [&](double (&r)[hp], int j0) {
+    double rinv = rcp_fast(__shfl_sync(FULLMASK, r[0], j0));
 #pragma unroll
-  for (int j = 0; j < m; j++) {
-    double *pb = buf + (j & 1) * m;
-    if (j < m - 1) {
+    for (int j = 0; j < hp; j++) {
+      double *pb = buf + (j & 1) * hp;
+      if (j < hp - 1) {
+        if (lane == j0 + j) {
+#pragma unroll
+          for (int k = (j + 1) & ~1; k < hp; k += 2) reinterpret_cast<double2 *>(pb)[k >> 1] = make_double2(r[k], r[k + 1]);
+        }
+        __syncwarp();
+      }
+      if (lane == j0 + j) {
+        myrd = rinv;
+        sing = !(fabs(r[j]) >= DBL_MIN);
+      }
+      const double l = (lane > j0 + j) ? r[j] * rinv : 0.0;
+      if (lane > j0 + j) r[j] = l;
+      if (j < hp - 1) {
+        r[j + 1] = fma(-l, pb[j + 1], r[j + 1]);
+        rinv = rcp_fast(__shfl_sync(FULLMASK, r[j + 1], j0 + j + 1));
+#pragma unroll
+        for (int k = (j + 2) & ~1; k < hp; k += 2) {
+          const double2 u = reinterpret_cast<const double2 *>(pb)[k >> 1];
+          if (k >= j + 2) r[k] = fma(-l, u.x, r[k]);
+          r[k + 1] = fma(-l, u.y, r[k + 1]);
+        }
+      }
+    }
+  };
+  auto store = [&](const double (&r)[hp], int c0) {
+#pragma unroll
+    for (int k = 0; k < hp; k++) {
+      const unsigned p = tposT[(c0 + k) * 32 + lane];
+      if (p != TNONE) Gc[p] = (c0 + k < lane) ? r[k] : (c0 + k == lane ? myrd : r[k] * myrd);
+    }
+  };
+  {   // ---- A
+    double r[hp];
+#pragma unroll
+    for (int k = 0; k < hp; k++) {
+      const unsigned p = tposT[k * 32 + lane];
+      r[k] = (p != TNONE) ? Gc[p] : 0.0;
+    }
+    factor(r, 0);
+#pragma unroll
+    for (int k = 0; k < hp; k++) lpan[k * 32 + lane] = (lane > k) ? r[k] : 0.0;
+    store(r, 0);
+  }
+  __syncwarp();
+  {   // ---- B, C
+    double s[hp];
+#pragma unroll
+    for (int k = 0; k < hp; k++) {
+      const unsigned p = tposT[(hp + k) * 32 + lane];
+      s[k] = (p != TNONE) ? Gc[p] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < hp; j++) {
+      double *pb = buf + (j & 1) * hp;
       if (lane == j) {
 #pragma unroll
-        for (int k = (j + 1) & ~1; k < m; k += 2) reinterpret_cast<double2 *>(pb)[k >> 1] = make_double2(r[k], r[k + 1]);
+        for (int k = 0; k < hp; k += 2) reinterpret_cast<double2 *>(pb)[k >> 1] = make_double2(s[k], s[k + 1]);
       }
       __syncwarp();
-    }
-    if (lane == j) {
-      myrd = rinv;
-      sing = !(fabs(r[j]) >= DBL_MIN);
-    }
-    const double l = (lane > j) ? r[j] * rinv : 0.0;
-    if (lane > j) r[j] = l;
-    if (j < m - 1) {
-      r[j + 1] = fma(-l, pb[j + 1], r[j + 1]);
-      rinv = rcp_fast(__shfl_sync(FULLMASK, r[j + 1], j + 1));
+      const double nl = -lpan[j * 32 + lane];
 #pragma unroll
-      for (int k = (j + 2) & ~1; k < m; k += 2) {
+      for (int k = 0; k < hp; k += 2) {
         const double2 u = reinterpret_cast<const double2 *>(pb)[k >> 1];
-        if (k >= j + 2) r[k] = fma(-l, u.x, r[k]);
-        r[k + 1] = fma(-l, u.y, r[k + 1]);
+        s[k] = fma(nl, u.x, s[k]);
+        s[k + 1] = fma(nl, u.y, s[k + 1]);
       }
     }
-  }
-#pragma unroll
-  for (int k = 0; k < m; k++) {
-    const unsigned p = tposT[k * 32 + lane];
-    if (p != TNONE) Gc[p] = (k < lane) ? r[k] : (k == lane ? myrd : r[k] * myrd);
+    __syncwarp();
+    factor(s, hp);
+    store(s, hp);
   }
   return __any_sync(FULLMASK, sing && lane < m);
 }
@@ -412,7 +462,7 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
   for (int k = gtid; k < L::NYG; k += GT)
     YG[k] = (k < M::NSPEC) ? 1.0 : (k < M::NSPEC + M::NLIT ? P.lit[k - M::NSPEC] : 1.0);
   for (int k = gtid; k <= M::NNZ; k += GT) G[k] = 0.0;
-  if (gtid == 0) { ctl->cell = -1; ctl->sing = 0; X[L::XPAD] = 0.0; }
+  if (gtid == 0) { ctl->cell = -1; ctl->sing = 0; X[L::XPAD] = 0.0; G[M::NNZ + 1] = 1.0; }
   __syncthreads();           // the only block barrier: the shared tables are in place
 
   const RosOpts &o = a.o;
@@ -453,14 +503,14 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
     gsync<WG>(group);
     WPROF(10);
     rd.at(sof[seg]);
-    run_phase<K_VDOT, WG>(rd, nbp[WP_VDOT], c BP(0));
+    run_phase<K_VDOT, WG>(rd, nbp[WP_VDOT], P.nlev[WP_VDOT], c BP(0));
   };
   // KppSolve on X in place (X visible to the group on entry and on return)
   auto solve = [&](int st) {
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
       rd.at(sof[WS_FWD0 + (st < 2 ? 2 * st : 3 * st - 1) + half]);
-      run_phase<K_SOLVE, WG>(rd, nbp[half ? WP_BWD : WP_FWD], c BP(3));
+      run_phase<K_SOLVE, WG>(rd, nbp[half ? WP_BWD : WP_FWD], P.nlev[half ? WP_BWD : WP_FWD], c BP(3));
       if (half == 0) {
         WPROF(7);
         if (lead) tail_solve<M>(G, X, tposT, diag, lane);
@@ -550,14 +600,14 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
           eval_terms<GT, 9>(bwt, rcsB, YG, SCR, m0, m1, gtid);
           gsync<WG>(group);
           rd.at(sof[half ? WS_JVS2 : WS_JVS]);
-          run_phase<K_JVS, WG>(rd, nbp[half ? WP_JVS2 : WP_JVS], c BP(1));
+          run_phase<K_JVS, WG>(rd, nbp[half ? WP_JVS2 : WP_JVS], P.nlev[half ? WP_JVS2 : WP_JVS], c BP(1));
         }
         WPROF(2);
         // ---- sparse LU (KppDecomp): head pivots from the stream, then the tail block in registers
         rd.at(sof[WS_LU]);
-        run_phase<K_LU, WG>(rd, nbp[WP_LU], c BP(2));
+        run_phase<K_LU, WG>(rd, nbp[WP_LU], P.nlev[WP_LU], c BP(2));
         WPROF(3);
-        if (lead && tail_lu<M>(G, X, tposT, lane)) ctl->sing = 1;
+        if (lead && tail_lu<M>(G, X, SCR, tposT, lane)) ctl->sing = 1;
         gsync<WG>(group);
         const bool sing = ctl->sing != 0;
         WPROF(4);
@@ -741,50 +791,47 @@ size_t warp_rcs_doubles_per_group(int mech_id)
   return mech_id == GCKPP_MECH_FULLCHEM ? (size_t)fullchem_dims::NREACT + fullchem_dims::NB : (size_t)Hg_dims::NREACT + Hg_dims::NB;
 }
 
-// One table phase split into per-warp row sequences: the bundles of a dependency level (wsched.py marks the
-// first bundle of a level with SYNC) are dealt round-robin to the WG warp-streams; in every stream the last
-// bundle of a level gets the SYNC flag (= group barrier after it); a stream without a bundle in a level gets
-// an empty one, so that all warps of a group execute the same number of barriers.
-static void deal_phase(const uint32_t *rows, int nrows, int wg, std::vector<std::vector<uint32_t>> &out, std::vector<int> &nb)
+// One table phase split into per-warp row sequences: bundle k of dependency level l (wsched.py marks the first
+// bundle of a level with SYNC) goes to warp-stream (k + l) % WG, so narrow levels rotate over the warps and every
+// warp streams about the same number of table rows.  In every stream the last bundle of a level gets the SYNC
+// flag (= group barrier after it); levels in which a stream has no bundle are counted in the PRE field of its
+// next bundle (that many barriers before it), trailing ones are made up by the kernel (it knows the level count).
+static int deal_phase(const uint32_t *rows, int nrows, int wg, std::vector<std::vector<uint32_t>> &out, std::vector<int> &nb, int &nlev)
 {
   out.assign(wg, {});
   nb.assign(wg, 0);
-  std::vector<std::vector<std::pair<int, int>>> level;          // per stream: (first row, rows) of its bundles in this level
-  auto flush = [&]() {
-    if (level.empty()) return;
-    for (int w = 0; w < wg; w++) {
-      if (level[w].empty()) {                                    // empty bundle: T = 0, nothing written
-        std::vector<uint32_t> row(128, 0u);
-        for (int l = 0; l < 32; l++) row[4 * l + 1] = F_SYNC;
-        out[w].insert(out[w].end(), row.begin(), row.end());
-        nb[w]++;
-        continue;
-      }
-      for (size_t i = 0; i < level[w].size(); i++) {
-        size_t at = out[w].size();
-        out[w].insert(out[w].end(), rows + (size_t)level[w][i].first * 128, rows + (size_t)(level[w][i].first + level[w][i].second) * 128);
-        for (int l = 0; l < 32; l++) {
-          uint32_t &meta = out[w][at + 4 * l + 1];
-          meta &= ~F_SYNC;
-          if (i + 1 == level[w].size()) meta |= F_SYNC;
-        }
-        nb[w]++;
-      }
-    }
-    level.clear();
-  };
-  int r = 0, k = 0;
-  while (r < nrows) {
+  std::vector<std::vector<std::pair<int, int>>> levels;         // (first row, rows) of the bundles of a level
+  for (int r = 0; r < nrows;) {
     const uint32_t meta = rows[(size_t)r * 128 + 1];
     const int T = meta & 63;
     const int n = 1 + (T > 2 ? (T - 2 + 3) / 4 : 0);
-    if (meta & F_SYNC) { flush(); k = 0; }
-    if (level.empty()) level.assign(wg, {});
-    level[k % wg].push_back({r, n});
-    k++;
+    if ((meta & F_SYNC) || levels.empty()) levels.push_back({});
+    levels.back().push_back({r, n});
     r += n;
   }
-  flush();
+  nlev = (int)levels.size();
+  std::vector<int> pre(wg, 0);
+  for (int l = 0; l < nlev; l++) {
+    std::vector<std::vector<std::pair<int, int>>> mine(wg);
+    for (size_t k = 0; k < levels[l].size(); k++) mine[(k + l) % wg].push_back(levels[l][k]);
+    for (int w = 0; w < wg; w++) {
+      if (mine[w].empty()) { pre[w]++; continue; }
+      if (pre[w] > PRE_MAX) return -6;
+      for (size_t i = 0; i < mine[w].size(); i++) {
+        size_t at = out[w].size();
+        out[w].insert(out[w].end(), rows + (size_t)mine[w][i].first * 128, rows + (size_t)(mine[w][i].first + mine[w][i].second) * 128);
+        for (int ln = 0; ln < 32; ln++) {
+          uint32_t &meta = out[w][at + 4 * ln + 1];
+          meta &= ~F_SYNC;
+          if (i == 0) meta |= (uint32_t)pre[w] << PRE_SHIFT;
+          if (i + 1 == mine[w].size()) meta |= F_SYNC;
+        }
+        nb[w]++;
+      }
+      pre[w] = 0;
+    }
+  }
+  return 0;
 }
 
 int warp_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_wsched_tables_t *S, WarpHostPlan &hp)
@@ -795,7 +842,8 @@ int warp_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_wsche
   const int wg = group_warps(mech_id);
   std::vector<std::vector<uint32_t>> ph[WARP_NPH];
   std::vector<int> nb[WARP_NPH];
-  for (int p = 0; p < WARP_NPH; p++) deal_phase(S->rows[p], S->nrows[p], wg, ph[p], nb[p]);
+  for (int p = 0; p < WARP_NPH; p++)
+    if (int rc = deal_phase(S->rows[p], S->nrows[p], wg, ph[p], nb[p], hp.nlev[p])) return rc;
   // the order one Rodas3 attempt consumes the tables in (NewF = T,F,T,T)
   static const int seg_phase[WARP_NSEG] = {WP_VDOT, WP_JVS, WP_JVS2, WP_LU, WP_FWD, WP_BWD, WP_FWD, WP_BWD, WP_VDOT, WP_FWD, WP_BWD,
                                            WP_VDOT, WP_FWD, WP_BWD};
@@ -813,7 +861,10 @@ int warp_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_wsche
     for (int sg = 0; sg < WARP_NSEG; sg++) if (hp.seg_off[w][sg] >= rows) hp.seg_off[w][sg] = 0;
     if (rows < 2 * RS) return -5;
     hp.w_rows[w] = rows;
+    // the rows of one attempt twice, plus the prefetch distance: the ring never wraps inside an attempt
     hp.stream.insert(hp.stream.end(), ws.begin(), ws.end());
+    hp.stream.insert(hp.stream.end(), ws.begin(), ws.end());
+    hp.stream.insert(hp.stream.end(), ws.begin(), ws.begin() + (size_t)RS * 128);
     for (int p = 0; p < WARP_NPH; p++) hp.nb[w][p] = nb[p][w];
   }
   hp.aw.resize(2 * (size_t)T->nreact);

@@ -32,11 +32,13 @@ struct WarpArgs {
   //   vdot jvs jvs2 lu fwd bwd fwd bwd vdot fwd bwd vdot fwd bwd
   // Every warp of a group has its own stream holding exactly that sequence of ITS bundles (cyclic), so the
   // ring prefetch never stalls on the common path.  The bundles of a dependency level are dealt round-robin
-  // to the warps; the last bundle of a warp in a level carries the SYNC flag (group barrier after it).
+  // to the warps; the last bundle of a warp in a level carries the SYNC flag (group barrier after it), the PRE field of a
+  // bundle counts the barriers of the levels before it in which the warp had no bundle.
   const uint4 *stream;                 // all per-warp streams, [rows][32]
   int w_off[WARP_WG], w_rows[WARP_WG]; // first row and length of warp-stream w
   int seg_off[WARP_WG][WARP_NSEG];     // first row of a segment, relative to the warp-stream
   int nb[WARP_WG][WARP_NPH];           // bundles of a phase in warp-stream w
+  int nlev[WARP_NPH];                  // dependency levels (= group barriers) of a phase
   const uint16_t *tpos;                // [32][32]
   const uint16_t *diag;                // [nvar] position of the diagonal
   const uint32_t *aw, *bw;             // [nreact][2], [nb][2] encoded rate / partial-derivative terms
@@ -52,6 +54,7 @@ struct WarpHostPlan {
   int w_off[WARP_WG], w_rows[WARP_WG];
   int seg_off[WARP_WG][WARP_NSEG];
   int nb[WARP_WG][WARP_NPH];
+  int nlev[WARP_NPH];
 };
 
 bool warp_kernel_supports(int mech_id);

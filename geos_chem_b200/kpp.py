@@ -98,11 +98,12 @@ def warp_plan(mech):
     stream = np.zeros((rows, 32, 4), np.uint32)
     if L.gckpp_gpu_warp_plan(MECH_ID[mech], info, 256, stream.ctypes.data_as(C.c_void_p), stream.size) != 0:
         raise KppError(L.gckpp_gpu_last_error().decode())
+    nlev = [int(x) for x in info[8:8 + nph]]
     warps = []
     for w in range(wg):
-        o = [int(x) for x in info[8 + w * per: 8 + (w + 1) * per]]
+        o = [int(x) for x in info[8 + nph + w * per: 8 + nph + (w + 1) * per]]
         warps.append(dict(off=o[0], rows=o[1], seg_off=o[2:2 + nseg], nb=o[2 + nseg:2 + nseg + nph]))
-    return dict(wg=wg, cells_per_block=cpb, smem_bytes=smem, ring_slots=rs, stream=stream, warps=warps)
+    return dict(wg=wg, cells_per_block=cpb, smem_bytes=smem, ring_slots=rs, stream=stream, warps=warps, nlev=nlev)
 
 
 def mech_dims(mech):

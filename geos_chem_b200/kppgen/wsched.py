@@ -31,8 +31,11 @@ segmented shuffle; sums are therefore re-associated with respect to the generate
 Table encoding, per lane a sequence of 16-byte rows (4 x uint32):
   row 0 of a bundle = (hdr, meta, t0, t1); further rows = (t2..t5), (t6..t9), ...
       rows = 1 + ceil(max(T - 2, 0) / 4);  the kernel executes exactly T terms
-  hdr  = target byte offset | aux byte offset << 16      (aux: the reciprocal pivot an L entry / a bwd row is scaled by)
-  meta = T | lg << 6 | SYNC << 9 | WRITE << 10 | MUL << 11 | DIAG << 12        (T, lg, SYNC uniform over the bundle)
+  hdr  = target byte offset | aux byte offset << 16      (aux: the reciprocal pivot an L entry / a bwd row is scaled by;
+         G slot NNZ+1 holds 1.0 for targets that are not scaled; lanes that write nothing target the 0.0 slot of the
+         array (G slot NNZ, X slot XPAD), so the kernel loads target and scale unconditionally)
+  meta = T | lg << 6 | SYNC << 9 | WRITE << 10 | MUL << 11 | DIAG << 12 | UDIAG << 18     (T, lg, SYNC, UDIAG uniform over
+         the bundle; bits 13-17 are filled in by the host plan)
   t    = hi << 16 | lo, BYTE offsets into the arrays of the phase:
            vdot/jvs: hi -> coefficient table, lo -> A / B scratch
            lu      : hi -> G (L(k,j)),        lo -> G (U(j,c))
@@ -49,6 +52,7 @@ TAIL = 32
 NONE = 0xFFFF
 
 F_SYNC, F_WRITE, F_MUL, F_DIAG = 1 << 9, 1 << 10, 1 << 11, 1 << 12
+F_UDIAG = 1 << 18          # uniform over the bundle: some lane has F_DIAG
 PHASES = ["vdot", "jvs", "jvs2", "lu", "fwd", "bwd"]
 
 
@@ -116,9 +120,11 @@ def conflict_degree(addrs):
 
 
 class Packer:
-    def __init__(self, pad, lmax=LMAX, optimise=True):
+    def __init__(self, pad, tzero, one, lmax=LMAX, optimise=True):
         self.bundles = []
         self.pad = pad
+        self.idle_hdr = tzero | (one << 16)     # lanes that write nothing: target = the 0.0 slot, scale = the 1.0 slot
+        self.one = one
         self.lmax = lmax
         self.optimise = optimise
 
@@ -138,7 +144,7 @@ class Packer:
             chunk = its[i:i + slots]
             i += slots
             lanes_terms = [[] for _ in range(32)]
-            hdr = [0] * 32
+            hdr = [self.idle_hdr] * 32
             flags = [0] * 32
             for s, (g, _, tgt, aux, fl, terms) in enumerate(chunk):
                 n = len(terms)
@@ -146,8 +152,9 @@ class Packer:
                 for p in range(G):
                     lane = s * G + p
                     lanes_terms[lane] = terms[p * per:(p + 1) * per] if per else []
-                    hdr[lane] = tgt | (aux << 16)
-                    flags[lane] = (fl | F_WRITE) if p == 0 else 0
+                    if p == 0:
+                        hdr[lane] = tgt | ((aux if fl & F_MUL else self.one) << 16)
+                        flags[lane] = fl | F_WRITE
             T = max(len(t) for t in lanes_terms)
             assert T < 64
             b = Bundle()
@@ -156,6 +163,8 @@ class Packer:
             b.sync = first
             first = False
             b.hdr = hdr
+            if any(f & F_DIAG for f in flags):
+                flags = [f | F_UDIAG for f in flags]
             b.flags = flags
             b.nreal = sum(len(t) for t in lanes_terms)
             if self.optimise and T > 0:
@@ -215,17 +224,20 @@ def run_rows(rows, hi_arr, lo_arr, tgt_arr, mode, ghinv=0.0):
             acc = acc + sh
         tg = (hdr & 0xffff) >> 3
         ax = (hdr >> 16) >> 3
+        assert np.all(((meta & F_UDIAG) != 0) == bool(np.any(meta & F_DIAG)))
+        old = tgt_arr[tg].copy()                 # the kernel loads target and scale of every lane
         for l in range(32):
             if not (meta[l] & F_WRITE):
+                assert old[l] == 0.0
                 continue
             if mode == "vdot":
                 tgt_arr[tg[l]] = acc[l]
             elif mode == "jvs":
-                tgt_arr[tg[l]] = (tgt_arr[tg[l]] - acc[l]) + (ghinv if (meta[l] & F_DIAG) else 0.0)
+                tgt_arr[tg[l]] = (old[l] - acc[l]) + (ghinv if (meta[l] & F_DIAG) else 0.0)
             else:
-                v = tgt_arr[tg[l]] - acc[l]
-                if meta[l] & F_MUL:
-                    v = v * hi_arr[ax[l]]
+                gmat = hi_arr                     # lu / solve: hi operands come from G
+                assert (meta[l] & F_MUL) or gmat[ax[l]] == 1.0
+                v = (old[l] - acc[l]) * gmat[ax[l]]
                 if meta[l] & F_DIAG:
                     if not (abs(v) >= np.finfo(np.float64).tiny):
                         sing = True
@@ -297,18 +309,19 @@ class WSchedule:
         self.coefs.append(0.0)                      # slot ncoef holds 0.0: padding terms of vdot / jvs
         self.coefs = np.array(self.coefs, np.float64)
         PAD_SUM = (ncoef * 8, 0)
-        PAD_G = (nnz * 8, nnz * 8)                  # G slot NNZ holds 0.0
+        PAD_G = (nnz * 8, nnz * 8)                  # G slot NNZ holds 0.0, slot NNZ+1 holds 1.0
+        GZERO, GONE, XZERO = nnz * 8, (nnz + 1) * 8, max(n, 64) * 8
         self.xpad = max(n, 64)                      # X slot XPAD holds 0.0 and is never written (X[0..63] doubles as a buffer)
         PAD_SOLVE = (nnz * 8, self.xpad * 8)
         self.phase = {}
 
-        P = Packer(PAD_SUM, lmax, optimise)
+        P = Packer(PAD_SUM, XZERO, GONE, lmax, optimise)
         P.add_level(vd)
         self.phase["vdot"] = P.bundles
-        P = Packer(PAD_SUM, lmax, optimise)
+        P = Packer(PAD_SUM, GZERO, GONE, lmax, optimise)
         P.add_level(jv)
         self.phase["jvs"] = P.bundles
-        P = Packer(PAD_SUM, lmax, optimise)
+        P = Packer(PAD_SUM, GZERO, GONE, lmax, optimise)
         if jv2:
             P.add_level(jv2)
         self.phase["jvs2"] = P.bundles
@@ -341,7 +354,7 @@ class WSchedule:
                     continue
                 lev[(k, c)] = lv + 1
                 levels.setdefault(lv + 1, []).append((p * 8, aux, fl, terms))
-        P = Packer(PAD_G, lmax, optimise)
+        P = Packer(PAD_G, GZERO, GONE, lmax, optimise)
         for lv in sorted(levels):
             P.add_level(levels[lv])
         self.phase["lu"] = P.bundles
@@ -358,7 +371,7 @@ class WSchedule:
             if i < h:
                 fl_[i] = lv
             levels.setdefault(lv, []).append((i * 8, 0, 0, terms))
-        P = Packer(PAD_SOLVE, lmax, optimise)
+        P = Packer(PAD_SOLVE, XZERO, GONE, lmax, optimise)
         for lv in sorted(levels):
             P.add_level(levels[lv])
         self.phase["fwd"] = P.bundles
@@ -372,7 +385,7 @@ class WSchedule:
             lv = 1 + max([bl[c] for c in Ur[i] if c < h], default=0)
             bl[i] = lv
             levels.setdefault(lv, []).append((i * 8, diag[i] * 8, F_MUL, terms))
-        P = Packer(PAD_SOLVE, lmax, optimise)
+        P = Packer(PAD_SOLVE, XZERO, GONE, lmax, optimise)
         for lv in sorted(levels):
             P.add_level(levels[lv])
         self.phase["bwd"] = P.bundles
@@ -419,12 +432,20 @@ class WSchedule:
         return sing
 
     def emulate_fun(self, A):
-        X = np.zeros(self.n)
+        X = self.xbuf(np.zeros(self.n))
         self.run_phase("vdot", self.coefs, A, X, "vdot")
-        return X
+        return X[:self.n]
+
+    def gbuf(self, g=None):
+        """the kernel's G array: LU_NONZERO entries, then the 0.0 and the 1.0 slot"""
+        G = np.zeros(self.nnz + 2)
+        if g is not None:
+            G[:self.nnz] = g[:self.nnz]
+        G[self.nnz + 1] = 1.0
+        return G
 
     def emulate_jac(self, B, ghinv):
-        G = np.zeros(self.nnz + 1)
+        G = self.gbuf()
         B = np.concatenate([B, np.zeros(2 * self.nscr - len(B))])
         self.run_phase("jvs", self.coefs, B[:self.nscr], G, "jvs", ghinv)
         self.run_phase("jvs2", self.coefs, B[self.nscr:], G, "jvs", ghinv)

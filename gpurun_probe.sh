@@ -1,8 +1,6 @@
 #!/bin/bash
-o=gpurun_out/r02d; mkdir -p $o
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ros_warp -c 1 -o $o/ros_warp_full -f \
-    python tools/variant_bench.py own kernel=2 > $o/ncu_full.log 2>&1
-ncu -i $o/ros_warp_full.ncu-rep --page raw --csv > $o/ros_warp_raw.csv 2>/dev/null
-ncu -i $o/ros_warp_full.ncu-rep --page details --csv > $o/ros_warp_details.csv 2>/dev/null
-ncu -i $o/ros_warp_full.ncu-rep --page source --csv > $o/ros_warp_source.csv 2>/dev/null
-ls -la $o; tail -3 $o/ncu_full.log
+o=gpurun_out/r02e; mkdir -p $o
+( timeout 600 python tests/gpu_tools/warp_debug.py grid ) > $o/warp_debug.log 2>&1
+tail -6 $o/warp_debug.log
+( timeout 300 python tools/variant_bench.py own kernel=2 ) > $o/variant.log 2>&1; echo "variant: $(tail -1 $o/variant.log)"
+( GCKPP_B200_LIB=geos_chem_b200/libgckpp_b200_prof.so GCKPP_PROFILE=1 timeout 120 python tools/smem_one.py 444 2 ) > $o/prof.log 2>&1; tail -6 $o/prof.log

@@ -42,20 +42,20 @@ def test_wschedule_matches_oracle(mech):
     jvs_o = o.jac(mech, C, R)
     ghinv = 1.0 / (300.0 * 0.5)
     G = s.emulate_jac(B, ghinv)
-    assert G[-1] == 0.0                       # the zero slot the padding terms point at
+    assert G[-2] == 0.0 and G[-1] == 1.0      # the slots padding terms / unscaled targets point at
     Gref = -jvs_o.copy()
     Gref[np.array(m.lu_diag)] += ghinv
-    np.testing.assert_allclose(G[:-1], Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
+    np.testing.assert_allclose(G[:-2], Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
     lu_o, ier = o.decomp(mech, Gref)
     assert ier == 0
     b = rng.standard_normal(m.nvar) * np.abs(vdot_o).max()
     x_o = o.solve(mech, lu_o, b)
-    Glu, sing = s.emulate_lu(np.append(Gref, 0.0))
-    assert not sing and Glu[-1] == 0.0
+    Glu, sing = s.emulate_lu(s.gbuf(Gref))
+    assert not sing and Glu[-2] == 0.0 and Glu[-1] == 1.0
     x = s.emulate_solve(Glu, b.copy())
     np.testing.assert_allclose(x, x_o, rtol=1e-9, atol=1e-12 * np.abs(x_o).max())
     d = np.array(m.lu_diag)
-    np.testing.assert_allclose(Glu[:-1][d], 1.0 / lu_o[d], rtol=1e-10)
+    np.testing.assert_allclose(Glu[:-2][d], 1.0 / lu_o[d], rtol=1e-10)
 
 
 def test_wschedule_structure():
@@ -84,7 +84,7 @@ def test_wschedule_structure():
         for reads, writes in levels:          # the bundles of a level run concurrently on the warps of a group
             assert not (reads & {(tk, t) for t in writes})
     # singular matrix is flagged
-    G = np.zeros(s.nnz + 1)
+    G = s.gbuf()
     G[np.array(m.lu_diag)] = 1.0
     G[m.lu_diag[5]] = 0.0
     _, sing = s.emulate_lu(G)
@@ -106,23 +106,31 @@ def test_host_plan_replay(mech, lib):
     PH = wsched.PHASES
 
     def seg_levels(w, seg):
-        """row chunks of warp-stream w for segment seg, one chunk per dependency level"""
+        """row chunks of warp-stream w for segment seg, one chunk (possibly empty) per dependency level"""
         W = plan["warps"][w]
         rows = plan["stream"][W["off"]:W["off"] + W["rows"]]
-        nb = W["nb"][PH.index(SEG[seg])]
-        r = W["seg_off"][seg]
+        ph = PH.index(SEG[seg])
+        nb, nlev = W["nb"][ph], plan["nlev"][ph]
+        r = W["seg_off"][seg] if nb else None
         out, cur = [], []
         for _ in range(nb):
             meta = int(rows[r, 0, 1]); T = meta & 63
             n = 1 + (max(T - 2, 0) + 3) // 4
+            pre = (meta >> 13) & 31
+            assert not (pre and cur), "barriers before a bundle only at the start of a level"
+            out.extend([None] * pre)             # levels without a bundle of this warp: barrier only
             cur.append(rows[r:r + n])
             r += n
             if meta & wsched.F_SYNC:
                 out.append(np.concatenate(cur)); cur = []
         assert not cur, "a warp-stream must end every level with a barrier"
-        # segments follow each other in the cyclic stream
-        nxt = W["seg_off"][(seg + 1) % len(SEG)]
-        assert r % W["rows"] == nxt
+        assert len(out) <= nlev
+        out.extend([None] * (nlev - len(out)))    # trailing barriers are made up by the kernel
+        if nb:                                    # segments follow each other in the cyclic stream
+            k = (seg + 1) % len(SEG)
+            while W["nb"][PH.index(SEG[k])] == 0:
+                k = (k + 1) % len(SEG)
+            assert r % W["rows"] == W["seg_off"][k]
         return out
 
     def replay(seg, hi, lo, tgt, mode, ghinv=0.0):
@@ -131,26 +139,31 @@ def test_host_plan_replay(mech, lib):
         sing = False
         for i in range(len(lv[0])):
             for w in reversed(range(wg)):          # any order within a level
-                sg, _ = wsched.run_rows(lv[w][i], hi, lo, tgt, mode, ghinv)
-                sing |= sg
+                if lv[w][i] is not None:
+                    sg, _ = wsched.run_rows(lv[w][i], hi, lo, tgt, mode, ghinv)
+                    sing |= sg
         return sing
+
+    if wg > 1:      # table rows are spread evenly over the warps of a group
+        rows = [W["rows"] for W in plan["warps"]]
+        assert max(rows) < 1.25 * min(rows), rows
 
     rng = np.random.default_rng(5)
     A = rng.standard_normal(m.nreact)
-    X = np.zeros(m.nvar)
+    X = s.xbuf(np.zeros(m.nvar))
     replay(0, s.coefs, A, X, "vdot")
-    np.testing.assert_array_equal(X, s.emulate_fun(A))
-    X2 = np.zeros(m.nvar)
+    np.testing.assert_array_equal(X[:m.nvar], s.emulate_fun(A))
+    X2 = s.xbuf(np.zeros(m.nvar))
     replay(8, s.coefs, A, X2, "vdot")
     np.testing.assert_array_equal(X2, X)
     B = rng.standard_normal(len(m.B))
     Bp = np.concatenate([B, np.zeros(2 * s.nscr - len(B))])
-    G = np.zeros(s.nnz + 1)
+    G = s.gbuf()
     replay(1, s.coefs, Bp[:s.nscr], G, "jvs", 0.25)
     replay(2, s.coefs, Bp[s.nscr:], G, "jvs", 0.25)
     np.testing.assert_array_equal(G, s.emulate_jac(B, 0.25))
     # a diagonally dominant matrix on the pattern
-    G = np.append(rng.standard_normal(s.nnz) * 0.1, 0.0)
+    G = s.gbuf(rng.standard_normal(s.nnz) * 0.1)
     G[np.array(m.lu_diag)] = 3.0 + rng.uniform(size=m.nvar)
     Gref, _ = s.emulate_lu(G.copy())
     Gw = G.copy()
