@@ -99,8 +99,7 @@ struct WLay {
   static constexpr int XPAD = cmax(M::NVAR, 64);           // X[XPAD] = 0.0, the operand of padding terms (never written)
   static constexpr int gSCR = gX + a128((XPAD + 1) * 8);   // X[0..63] doubles as the pivot-row buffer of tail_lu
   static constexpr int gCTL = gSCR + a128(cmax(NSCR * 8, 16 * 32 * 8));   // SCR doubles as the L panel of tail_lu
-  static constexpr int gRING = gCTL + a128((int)sizeof(GCtl));
-  static constexpr int GSZ = gRING + WG * RS * 512;
+  static constexpr int GSZ = gCTL + a128((int)sizeof(GCtl));
   static constexpr int NGRP = cmin(cmin(1024 / GT, WG == 1 ? 16 : 15), (SMEM_LIMIT - oGRP) / GSZ);
   static constexpr int TOTAL = oGRP + NGRP * GSZ;
   static constexpr int NQ = (M::NSPEC + GT - 1) / GT;
@@ -115,43 +114,28 @@ __device__ __forceinline__ void gsync(int group)
   else asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(WG * 32) : "memory");
 }
 
-// ---- streamed tables: 16 bytes per lane per row, cp.async ring ----------------------------------------
-// The stream of a warp holds the rows of one attempt TWICE (+ RS rows), so the prefetch never has to wrap inside
-// an attempt: `pos` is folded back by L at the start of a phase only.  Slot k of the ring is refilled right after
-// it has been read (the copy lands hundreds of cycles after the read has executed).
+// ---- streamed tables: 16 bytes per lane per row, read straight from L2 into a three-row register window ----
+// (A cp.async ring through shared memory costs 8 shared-memory wavefronts per row -- a quarter of the kernel's LSU
+// traffic -- and is limited to one row per ~100-165 cycles per warp; ld.global.cg costs 4 and pipelines.)
+// The window always holds rows pos, pos+1, pos+2: the rows of the NEXT bundle are requested while the current one
+// is being processed.  The stream of a warp holds the rows of one attempt TWICE (+ a few rows), so `pos` never has
+// to wrap inside a phase: it is folded back by L at the start of a phase only.
 struct WReader {
   const uint4 *gsrc;        // this lane's column of the warp's stream
-  uint32_t ring;            // shared-space byte address of this lane's column of the warp's ring
-  int L, pos, slot;         // rows of one attempt, next row to consume, its ring slot
-  __device__ __forceinline__ void seek(int row)
-  {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-    pos = row; slot = 0;
-#pragma unroll
-    for (int i = 0; i < RS; i++)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
-                   :: "r"(ring + i * 512), "l"(gsrc + (size_t)(row + i) * 32) : "memory");
-  }
+  int L, pos;               // rows of one attempt, row held in w0
+  uint4 w0, w1, w2;
+  __device__ __forceinline__ uint4 ld(int row) const { return __ldcg(gsrc + (size_t)row * 32); }
+  __device__ __forceinline__ void seek(int row) { pos = row; w0 = ld(row); w1 = ld(row + 1); w2 = ld(row + 2); }
   // the stream is consumed in the fixed order of an accepted attempt; anything else (rejected step,
-  // singular matrix, failed cell) re-positions the ring
+  // singular matrix, failed cell) re-positions the window
   __device__ __forceinline__ void at(int row)
   {
     if (pos >= L) pos -= L;
     if (pos != row) seek(row);
   }
-  __device__ __forceinline__ uint4 next()
-  {
-    uint4 v;
-    const uint32_t sa = ring + slot * 512;
-    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 1) : "memory");
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
-                 :: "r"(sa), "l"(gsrc + (size_t)(pos + RS) * 32) : "memory");
-    pos++;
-    if (++slot == RS) slot = 0;
-    return v;
-  }
+  __device__ __forceinline__ void advance1() { w0 = w1; w1 = w2; w2 = ld(pos + 3); pos += 1; }
+  __device__ __forceinline__ void advance2() { w0 = w2; w1 = ld(pos + 3); w2 = ld(pos + 4); pos += 2; }
+  __device__ __forceinline__ void advance3() { w0 = ld(pos + 3); w1 = ld(pos + 4); w2 = ld(pos + 5); pos += 3; }
 };
 
 struct WCtx {
@@ -202,7 +186,7 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c
   unsigned char *Tb = (KIND == K_VDOT || KIND == K_SOLVE) ? c.Xb : c.Gb;
 #pragma unroll 1
   for (int b = 0; b < nb; b++) {
-    const uint4 r0 = rd.next();
+    const uint4 r0 = rd.w0;
     const unsigned hdr = r0.x, meta = r0.y;
     const int T = meta & 63, lg = (meta >> 6) & 7;
     const bool wr = (meta & F_WRITE) != 0;
@@ -217,17 +201,19 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c
 #define LDT(w, hv, lv) const double hv = ldb(Hb, (w) >> 16), lv = ldb(Lb, (w) & 0xffffu)
 #define LDP(p, w, hv, lv) double hv = 0.0, lv = 0.0; if (p) { hv = ldb(Hb, (w) >> 16); lv = ldb(Lb, (w) & 0xffffu); }
     if (T <= 2) {                       // one table row
+      rd.advance1();
       LDP(T > 0, r0.z, h0, l0) LDP(T > 1, r0.w, h1, l1)
       a0 = h0 * l0; a1 = h1 * l1;
     } else if (T <= 6) {                // two table rows
-      const uint4 r1 = rd.next();
+      const uint4 r1 = rd.w1;
+      rd.advance2();
       LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2);
       LDP(T > 3, r1.y, h3, l3) LDP(T > 4, r1.z, h4, l4) LDP(T > 5, r1.w, h5, l5)
       a0 = h0 * l0; a1 = h1 * l1; a2 = h2 * l2; a3 = h3 * l3;
       a0 = fma(h4, l4, a0); a1 = fma(h5, l5, a1);
     } else {                            // three table rows, and a loop for the rare longer lane
-      const uint4 r1 = rd.next();
-      uint4 r2 = rd.next();
+      const uint4 r1 = rd.w1, r2 = rd.w2;
+      rd.advance3();
       LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2); LDT(r1.y, h3, l3); LDT(r1.z, h4, l4); LDT(r1.w, h5, l5);
       LDT(r2.x, h6, l6);
       LDP(T > 7, r2.y, h7, l7) LDP(T > 8, r2.z, h8, l8) LDP(T > 9, r2.w, h9, l9)
@@ -236,9 +222,10 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c
       a0 = fma(h8, l8, a0); a1 = fma(h9, l9, a1);
 #pragma unroll 1
       for (int k = 10; k < T; k += 4) {
-        r2 = rd.next();
-        LDT(r2.x, g0, m0);
-        LDP(k + 1 < T, r2.y, g1, m1) LDP(k + 2 < T, r2.z, g2, m2) LDP(k + 3 < T, r2.w, g3, m3)
+        const uint4 r3 = rd.w0;
+        rd.advance1();
+        LDT(r3.x, g0, m0);
+        LDP(k + 1 < T, r3.y, g1, m1) LDP(k + 2 < T, r3.z, g2, m2) LDP(k + 3 < T, r3.w, g3, m3)
         a0 = fma(g0, m0, a0); a1 = fma(g1, m1, a1); a2 = fma(g2, m2, a2); a3 = fma(g3, m3, a3);
       }
     }
@@ -477,7 +464,6 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
   c.ctl = ctl; c.ghinv = 0.0; c.group = group;
   WReader rd;
   rd.gsrc = P.stream + (size_t)P.w_off[sw] * 32 + lane;
-  rd.ring = (uint32_t)__cvta_generic_to_shared(gb + L::gRING + (wig * RS) * 512 + lane * 16);
   rd.L = P.w_rows[sw];
   rd.seek(0);
   int nbp[WARP_NPH], sof[WARP_NSEG];
@@ -755,7 +741,6 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
     atomicAdd(a.sums + 2, acc_fail);
     atomicAdd(a.sums + 3, acc_done);
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 }  // namespace
