@@ -91,6 +91,8 @@ struct DevBuf {
   template <class T> T *as() { return (T *)p; }
 };
 
+struct WaveSlot;
+static void free_slots(struct gckpp_gpu_handle *h);
 struct gckpp_gpu_handle {
   int mech_id = 0, device = 0, max_cells = 0;
   const gckpp_host_tables_t *T = nullptr;
@@ -105,7 +107,7 @@ struct gckpp_gpu_handle {
   DevBuf work, next, sums, tol, cell_list, counter, rconst_work, scratch;
   // staging for the host entry points
   DevBuf s_conc_in, s_conc_out, s_rconst, s_met, s_photol, s_khet, s_hstart, s_active, s_ist, s_rst, s_ierr;
-  int opt_retry = 0, opt_kernel = -1, opt_sort = 0;
+  int opt_retry = 0, opt_kernel = -1, opt_wave_cells = 0, opt_pin = 0, opt_dev_wave = 0;
   // shared-memory kernel: host plan + device copies of its tables
   int sm_ready = 0, sm_blocks_cap = 0;
   SmemHostPlan plan;
@@ -122,7 +124,8 @@ struct gckpp_gpu_handle {
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
   DevBuf ident; int ident_n = 0;
-  int opt_chunks = 4;
+  int opt_chunks = 0;
+  struct WaveSlot *slots = nullptr;
   double stats[16]{};
 };
 
@@ -236,6 +239,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
                     &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
+  free_slots(h);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -267,10 +271,12 @@ extern "C" int gckpp_gpu_set_option(gckpp_gpu_handle_t *h, const char *key, int 
   if (!h || !key) return fail(-10, "gckpp_gpu_set_option: NULL argument");
   if (!strcmp(key, "retry")) h->opt_retry = value;
   else if (!strcmp(key, "kernel")) h->opt_kernel = value;
-  else if (!strcmp(key, "sort")) h->opt_sort = value;
+  else if (!strcmp(key, "wave_cells")) { if (value < 0) return fail(-10, "wave_cells out of range"); h->opt_wave_cells = value; }
+  else if (!strcmp(key, "pin")) h->opt_pin = value;
+  else if (!strcmp(key, "device_wave_cells")) { if (value < 0) return fail(-10, "device_wave_cells out of range"); h->opt_dev_wave = value; }
   else if (!strcmp(key, "blocks_per_sm")) { if (value < 1 || value > 16) return fail(-10, "blocks_per_sm out of range"); h->blocks_per_sm = value; h->max_blocks = h->sm_count * value; }
   else if (!strcmp(key, "blocks_cap")) { h->sm_blocks_cap = value; }
-  else if (!strcmp(key, "chunks")) { if (value < 1 || value > 64) return fail(-10, "chunks out of range"); h->opt_chunks = value; }
+  else if (!strcmp(key, "chunks")) { if (value < 0 || value > 4096) return fail(-10, "chunks out of range"); h->opt_chunks = value; }
   else if (!strcmp(key, "threads")) { if (value < 32 || value > 1024 || value % 32) return fail(-10, "threads must be a multiple of 32"); h->threads = value; }
   else return fail(-10, "gckpp_gpu_set_option: unknown option '%s'", key);
   return 0;
@@ -522,13 +528,16 @@ static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
   if (h->T->nnz <= 0) return 0;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return 0;
   if (d.o.Tstart == d.o.Tend) return 0;
-  if (h->opt_kernel == 1) return (host_sched(h->mech_id) && smem_kernel_supports(h->mech_id)) ? 1 : 0;
-  return (host_wsched(h->mech_id) && warp_kernel_supports(h->mech_id)) ? 2 : 0;
+  // "kernel"=2: the warp-group kernel -- on explicit request only: its results vary from run to run at the 1e-9
+  // level (37 % of the cells, tests/gpu_tools/determinism.py), the block-synchronous kernel's never do
+  if (h->opt_kernel == 2) return (host_wsched(h->mech_id) && warp_kernel_supports(h->mech_id)) ? 2 : 0;
+  return (host_sched(h->mech_id) && smem_kernel_supports(h->mech_id)) ? 1 : 0;
 }
 
 static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int nwork, const int *cell_list,
                           const double *conc_in, const double *rconst, const double *hstart,
-                          double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+                          double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr,
+                          int rc_stride = 0, int rc_cell0 = 0)
 {
   if (nwork <= 0) return 0;
   const int kern = choose_kernel(h, d);
@@ -540,6 +549,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   RosArgs a;
   a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
   a.conc_in = conc_in; a.rconst = rconst; a.hstart = hstart;
+  a.rc_stride = rc_stride > 0 ? rc_stride : ncell; a.rc_cell0 = rc_cell0;
   a.atol = h->tol.as<double>(); a.rtol = h->tol.as<double>() + h->T->nvar;
   a.conc_out = conc_out; a.istatus = istatus; a.rstatus = rstatus; a.ierr = ierr;
   a.work = h->work.as<double>(); a.ws_stride = (size_t)h->L.total * 32;
@@ -573,6 +583,132 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   return 0;
 }
 
+// The arrays of one call (or one wave of a call) on the device; every per-cell array has row stride n.
+struct DevIO {
+  const double *conc_in, *rconst, *temp, *numden, *h2o, *photol, *khet, *hstart;
+  const uint8_t *active;
+  double *conc_out; int32_t *istatus; double *rstatus; int32_t *ierr;
+  double *rconst_work;        // [NREACT][n] scratch for Update_RCONST when rconst == NULL
+};
+
+static void print_profile(gckpp_gpu_handle *h, const unsigned long long *sums)
+{
+  if (h->last_kernel == 2) {
+    fprintf(stderr, "[gckpp profile] lead warp of group 0, block 0, cycles: load %llu fun0(vdot) %llu jac %llu lu_head %llu lu_tail %llu tail_solve %llu stage_rhs+vdot %llu solve_streams %llu accept %llu retire %llu rates %llu\n",
+            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18]);
+    const char *kn[4] = {"vdot", "jvs", "lu", "solve"};
+    for (int k = 0; k < 4; k++)
+      fprintf(stderr, "[gckpp profile]   %-5s bundles %llu: table wait %llu operands+fma %llu shuffles %llu store %llu barrier %llu\n", kn[k],
+              sums[20 + 6 * k + 5], sums[20 + 6 * k + 0], sums[20 + 6 * k + 1], sums[20 + 6 * k + 2], sums[20 + 6 * k + 3], sums[20 + 6 * k + 4]);
+  } else {
+    fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
+            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
+            sums[20], sums[21], sums[22], sums[23]);
+  }
+}
+
+// One batch of n cells on the device: Update_RCONST (when no rate constants are given), the InChemGrid mask, the
+// integration, and Do_FullChem's retry.  The counters in h->sums accumulate over the batches of a call (the caller
+// clears them once); the handle stream is synchronised only when a count has to reach the host (mask, retry).
+// stats[4] / stats[5] accumulate the retried / failed-twice cells.
+static int device_core(gckpp_gpu_handle *h, const Decoded &d, int n, const DevIO &io, unsigned long long *fails_before)
+{
+  const gckpp_host_tables_t *T = h->T;
+  if (!io.rconst && (!io.temp || !io.numden || !io.h2o)) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
+  // When the rate constants are computed here they live in a scratch of at most `device_wave_cells` columns
+  // (8.5 KB per cell for fullchem): a batch larger than that is walked through in cell ranges.
+  const int DW = io.rconst ? n : (h->opt_dev_wave > 0 ? h->opt_dev_wave : (1 << 20));
+  const bool ranged = n > DW;
+  if ((ranged || io.active || h->opt_retry) && h->cell_list.ensure(sizeof(int) * (size_t)n)) return fail(-1002, "out of device memory");
+  if (ranged && !io.active) {
+    if (h->ident.ensure(sizeof(int) * (size_t)n)) return fail(-1002, "out of device memory");
+    if (h->ident_n < n) { CUDA_TRY(launch_iota(h->ident.as<int>(), n, h->stream)); h->ident_n = n; }
+  }
+  for (int c0 = 0; c0 < n; c0 += DW) {
+    const int m = (c0 + DW <= n) ? DW : n - c0, c1 = c0 + m;
+    const double *rconst = io.rconst;
+    int rc_stride = n, rc_cell0 = 0;
+    if (!rconst) {
+      CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+      CUDA_TRY(launch_update_rconst(h->mech_id, m, io.temp + c0, io.numden + c0, io.h2o + c0, io.photol ? io.photol + c0 : nullptr,
+                                    io.khet ? io.khet + c0 : nullptr, io.rconst_work, h->stream, /*input stride*/ n, /*output stride*/ m));
+      CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+      h->stats[6] += 1;
+      h->stats[12] += 1;          // Update_RCONST launches of this call
+      rconst = io.rconst_work; rc_stride = m; rc_cell0 = c0;
+    }
+    // cells outside the chemistry grid: copy through, zero status
+    const int *cell_list = nullptr;
+    int nwork = m;
+    if (io.active) {
+      CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+      CUDA_TRY(launch_select_active(n, c0, c1, io.active, T->nspec, io.conc_in, io.conc_out, io.istatus, io.rstatus, io.ierr,
+                                    h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
+      h->stats[6] += 1;
+      CUDA_TRY(cudaMemcpyAsync(&nwork, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      cell_list = h->cell_list.as<int>();
+    } else if (ranged) {
+      cell_list = h->ident.as<int>() + c0;
+    }
+    int rc = run_integrator(h, d, n, nwork, cell_list, io.conc_in, rconst, io.hstart, io.conc_out, io.istatus, io.rstatus, io.ierr,
+                            rc_stride, rc_cell0);
+    if (rc) return rc;
+    // Do_FullChem's retry (fullchem_mod.F90:1138-1162): C restored, RCNTRL(3) = 0, integrate again.  (The reference
+    // also sets RCNTRL(12) = -1 to switch auto-reduce off, but Integrate's merge drops non-positive RCNTRL values
+    // (gckpp_Integrator.F90:116), so auto-reduce stays on for the retry there too: SURVEY Q3.)
+    if (h->opt_retry && io.ierr) {
+      unsigned long long sums[4];
+      CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      const int nfail = (int)(sums[2] - *fails_before);
+      if (nfail > 0) {
+        CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
+        CUDA_TRY(launch_select_failed(c0, c1, io.ierr, h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
+        int nretry = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nretry, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        Decoded d2 = d;
+        d2.o.Hstart_rcntrl = 0.0;
+        rc = run_integrator(h, d2, n, nretry, h->cell_list.as<int>(), io.conc_in, rconst, nullptr, io.conc_out, io.istatus,
+                            io.rstatus, io.ierr, rc_stride, rc_cell0);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->stats[4] += nretry;
+        h->stats[5] += (double)(sums[2] - *fails_before - (unsigned long long)nfail);    // failed again
+        h->stats[6] += 1;
+      }
+      *fails_before = sums[2];
+    }
+  }
+  return 0;
+}
+
+// option checks shared by the entry points; fills ierr on the reference's own option errors (-1..-5)
+static int check_decoded(gckpp_gpu_handle *h, const Decoded &d)
+{
+  if (d.autoreduce && d.ICNTRL[12] == 1) return fail(-12, "the append variant of auto-reduce (ICNTRL(13)=1) is not available in this build");
+  if (d.autoreduce && !h->T->fun_split) return fail(-12, "auto-reduce needs the split ODE function (fullchem)");
+  return 0;
+}
+
+static int finish_stats(gckpp_gpu_handle *h)
+{
+  unsigned long long sums[64];
+  CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (getenv("GCKPP_PROFILE")) print_profile(h, sums);
+  h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
+  h->stats[10] = (double)sums[2];           // integrations that ended with IERR < 0 (first pass and retry)
+  if (h->stats[12] > 0) {                   // Update_RCONST: the last launch's time, scaled to the launches of the call
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->stats[1] = ms * h->stats[12];
+    else cudaGetLastError();
+  }
+  return 0;
+}
+
 extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, double tin, double tout,
                                           const double *conc_in, const double *rconst,
                                           const double *temp, const double *numden, const double *h2o,
@@ -594,209 +730,82 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return rc;
   }
-  if (d.autoreduce && d.ICNTRL[12] == 1) return fail(-12, "the append variant of auto-reduce (ICNTRL(13)=1) is not available in this build");
-  if (d.autoreduce && !T->fun_split) return fail(-12, "auto-reduce needs the split ODE function (fullchem)");
+  if ((rc = check_decoded(h, d))) return rc;
   for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
   if (atol && rtol) {
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
-
-  // K1: rate constants
+  {
+    const size_t dw = (size_t)(h->opt_dev_wave > 0 ? h->opt_dev_wave : (1 << 20));
+    if (!rconst && h->rconst_work.ensure(sizeof(double) * (size_t)T->nreact * ((size_t)ncell < dw ? (size_t)ncell : dw))) return fail(-1002, "out of device memory for rconst");
+  }
+  DevIO io{conc_in, rconst, temp, numden, h2o, photol, khet, hstart, active, conc_out, istatus, rstatus, ierr,
+           h->rconst_work.as<double>()};
   CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
-  if (!rconst) {
-    if (!temp || !numden || !h2o) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
-    if (h->rconst_work.ensure(sizeof(double) * (size_t)T->nreact * ncell)) return fail(-1002, "out of device memory for rconst");
-    CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, h->rconst_work.as<double>(), h->stream));
-    h->stats[6] += 1;
-    rconst = h->rconst_work.as<double>();
-  }
-  CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
-
-  // cells outside the chemistry grid: copy through, zero status
-  const int *cell_list = nullptr;
-  int nwork = ncell;
-  if (active) {
-    if (h->cell_list.ensure(sizeof(int) * (size_t)ncell)) return fail(-1002, "out of device memory");
-    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    CUDA_TRY(launch_select_active(ncell, active, T->nspec, conc_in, conc_out, istatus, rstatus, ierr,
-                                  h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
-    h->stats[6] += 1;
-    CUDA_TRY(cudaMemcpyAsync(&nwork, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cell_list = h->cell_list.as<int>();
-  }
-  rc = run_integrator(h, d, ncell, nwork, cell_list, conc_in, rconst, hstart, conc_out, istatus, rstatus, ierr);
-  if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
-
-  unsigned long long sums[64];
-  CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (getenv("GCKPP_PROFILE")) {
-    if (h->last_kernel == 2) {
-      fprintf(stderr, "[gckpp profile] lead warp of group 0, block 0, cycles: load %llu fun0(vdot) %llu jac %llu lu_head %llu lu_tail %llu tail_solve %llu stage_rhs+vdot %llu solve_streams %llu accept %llu retire %llu rates %llu\n",
-              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18]);
-      const char *kn[4] = {"vdot", "jvs", "lu", "solve"};
-      for (int k = 0; k < 4; k++)
-        fprintf(stderr, "[gckpp profile]   %-5s bundles %llu: table wait %llu operands+fma %llu shuffles %llu store %llu barrier %llu\n", kn[k],
-                sums[20 + 6 * k + 5], sums[20 + 6 * k + 0], sums[20 + 6 * k + 1], sums[20 + 6 * k + 2], sums[20 + 6 * k + 3], sums[20 + 6 * k + 4]);
-    }
-    else
-      fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
-              sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
-              sums[20], sums[21], sums[22], sums[23]);
-  }
-  int nfail = (int)sums[2], nfail2 = 0;
-  h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
-
-  // Do_FullChem's retry (fullchem_mod.F90:1138-1162): RCNTRL(3)=0, C restored, integrate again
-  if (h->opt_retry && nfail > 0 && ierr) {
-    if (h->cell_list.ensure(sizeof(int) * (size_t)ncell)) return fail(-1002, "out of device memory");
-    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(int), h->stream));
-    CUDA_TRY(launch_select_failed(ncell, ierr, h->cell_list.as<int>(), h->counter.as<int>(), h->stream));
-    int nretry = 0;
-    CUDA_TRY(cudaMemcpyAsync(&nretry, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    Decoded d2 = d;
-    d2.o.Hstart_rcntrl = 0.0;
-    CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
-    rc = run_integrator(h, d2, ncell, nretry, h->cell_list.as<int>(), conc_in, rconst, nullptr, conc_out, istatus, rstatus, ierr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    nfail2 = (int)sums[2];
-    h->stats[4] = nretry; h->stats[5] = nfail2;
-    h->stats[6] += 1;
-  } else {
-    h->stats[5] = 0;
-  }
+  unsigned long long fails = 0;
+  if ((rc = device_core(h, d, ncell, io, &fails))) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = finish_stats(h))) return rc;
   float ms = 0;
-  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->stats[0] = ms;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->stats[1] = ms;
-  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->stats[9] = ms;
-  return h->opt_retry ? nfail2 : 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]);
+  h->stats[0] = ms; h->stats[9] = ms;
+  return h->opt_retry ? (int)h->stats[5] : 0;
 }
 
-// ---- host-buffer entry: stage through device buffers ------------------------------------
-static int h2d(gckpp_gpu_handle *h, DevBuf &b, const void *src, size_t bytes)
-{
-  if (b.ensure(bytes)) return fail(-1002, "out of device memory (%zu MB)", bytes >> 20);
-  CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
-  return 0;
-}
+// ---- host-buffer entry ------------------------------------------------------------------------------------
+// The cells are processed in WAVES of at most `wave_cells` cells (contiguous cell ranges; every per-cell array is
+// [rows][ncell] cell-fastest, so a wave is a 2-D copy with pitch ncell).  Device memory is bounded by two waves, whatever
+// the grid (C180: 14 M cells), and the copies overlap the integration: while wave i integrates on the handle stream,
+// the inputs of wave i+1 travel to the device on the copy-in stream and the results of wave i-1 travel back on the
+// copy-out stream.  This is the batched replacement of the cell loop of Do_FullChem (fullchem_mod.F90:528-1551): one
+// call per chemistry step per GPU, as GCHP calls the routine once per tile (gchp_chunk_mod.F90:1366).
+struct WaveSlot {
+  DevBuf conc_in, conc_out, rconst, met, photol, khet, hstart, active, ist, rst, ierr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+};
 
-
-// Host-buffer entry, pipelined: the cells are cut into `chunks` contiguous ranges; the slices of chunk i+1 are
-// copied to the device (copy-in stream) while chunk i integrates (handle stream) and the results of chunk i-1
-// travel back (copy-out stream).  Every per-cell array is [rows][ncell] cell-fastest, so a chunk is a 2-D copy
-// with pitch ncell*8.  Used when there is no `active` mask and no retry (those need the whole-grid lists).
-static int integrate_pipelined(gckpp_gpu_handle *h, int ncell, double tin, double tout,
-                               const double *conc_in, const double *rconst,
-                               const double *temp, const double *numden, const double *h2o,
-                               const double *photol, const double *khet,
-                               const double *atol, const double *rtol,
-                               const int32_t *icntrl, const double *rcntrl, const double *hstart,
-                               double *conc_out, int32_t *istatus, double *rstatus, int32_t *ierr)
+static int ensure_slots(gckpp_gpu_handle *h)
 {
-  const gckpp_host_tables_t *T = h->T;
-  const size_t nc = (size_t)ncell;
-  Decoded d;
-  int rc = decode_options(T, tin, tout, icntrl, rcntrl, atol, rtol, d);
-  if (rc) {
-    if (ierr && rc >= -5) for (size_t i = 0; i < nc; i++) ierr[i] = rc;
-    return rc;
+  if (h->slots) return 0;
+  h->slots = new WaveSlot[2];
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&h->slots[i].ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->slots[i].ev_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->slots[i].ev_out, cudaEventDisableTiming));
   }
-  if (d.autoreduce && d.ICNTRL[12] == 1) return fail(-12, "the append variant of auto-reduce (ICNTRL(13)=1) is not available in this build");
-  if (d.autoreduce && !T->fun_split) return fail(-12, "auto-reduce needs the split ODE function (fullchem)");
-  if (!rconst && (!temp || !numden || !h2o)) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
   if (!h->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   if (!h->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
-  const bool have_ph = photol && T->nphot, have_kh = khet && T->next;
-  if (h->s_conc_in.ensure(sizeof(double) * T->nspec * nc) || h->s_conc_out.ensure(sizeof(double) * T->nspec * nc) ||
-      h->s_ist.ensure(sizeof(int) * 8 * nc) || h->s_rst.ensure(sizeof(double) * 4 * nc) || h->s_ierr.ensure(sizeof(int) * nc) ||
-      h->s_met.ensure(3 * sizeof(double) * nc) || (hstart && h->s_hstart.ensure(sizeof(double) * nc)) ||
-      (have_ph && h->s_photol.ensure(sizeof(double) * T->nphot * nc)) || (have_kh && h->s_khet.ensure(sizeof(double) * T->next * nc)) ||
-      (rconst ? h->s_rconst.ensure(sizeof(double) * T->nreact * nc) : h->rconst_work.ensure(sizeof(double) * T->nreact * nc)) ||
-      h->ident.ensure(sizeof(int) * nc))
-    return fail(-1002, "out of device memory");
-  if (h->ident_n < ncell) {
-    CUDA_TRY(launch_iota(h->ident.as<int>(), ncell, h->stream));
-    h->ident_n = ncell;
-  }
-  CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
-  double *d_temp = h->s_met.as<double>(), *d_numden = d_temp + nc, *d_h2o = d_numden + nc;
-  double *d_rc = rconst ? h->s_rconst.as<double>() : h->rconst_work.as<double>();
-  const int K = h->opt_chunks;
-  std::vector<cudaEvent_t> ev_in(K), ev_done(K);
-  for (int i = 0; i < K; i++) {
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-  }
-  const size_t pitch = sizeof(double) * nc;
-  auto rows_in = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt, cudaStream_t st) {
-    return cudaMemcpy2DAsync((char *)dst + c0 * elt, nc * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows,
-                             cudaMemcpyHostToDevice, st);
-  };
-  auto rows_out = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt, cudaStream_t st) {
-    return cudaMemcpy2DAsync((char *)dst + c0 * elt, nc * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows,
-                             cudaMemcpyDeviceToHost, st);
-  };
-  (void)pitch;
-  CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-  // copy-in of every chunk is queued up front; the copy stream runs ahead of the compute stream
-  for (int i = 0; i < K; i++) {
-    const size_t c0 = nc * i / K, n = nc * (i + 1) / K - c0;
-    CUDA_TRY(rows_in(h->s_conc_in.p, conc_in, c0, n, T->nspec, 8, h->s_in));
-    if (rconst) CUDA_TRY(rows_in(h->s_rconst.p, rconst, c0, n, T->nreact, 8, h->s_in));
-    if (temp && numden && h2o) {
-      CUDA_TRY(rows_in(d_temp, temp, c0, n, 1, 8, h->s_in));
-      CUDA_TRY(rows_in(d_numden, numden, c0, n, 1, 8, h->s_in));
-      CUDA_TRY(rows_in(d_h2o, h2o, c0, n, 1, 8, h->s_in));
-    }
-    if (have_ph) CUDA_TRY(rows_in(h->s_photol.p, photol, c0, n, T->nphot, 8, h->s_in));
-    if (have_kh) CUDA_TRY(rows_in(h->s_khet.p, khet, c0, n, T->next, 8, h->s_in));
-    if (hstart) CUDA_TRY(rows_in(h->s_hstart.p, hstart, c0, n, 1, 8, h->s_in));
-    CUDA_TRY(cudaEventRecord(ev_in[i], h->s_in));
-  }
-  CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
-  for (int i = 0; i < K; i++) {
-    const size_t c0 = nc * i / K, n = nc * (i + 1) / K - c0;
-    CUDA_TRY(cudaStreamWaitEvent(h->stream, ev_in[i], 0));
-    if (!rconst) {
-      CUDA_TRY(launch_update_rconst(h->mech_id, (int)n, d_temp + c0, d_numden + c0, d_h2o + c0,
-                                    have_ph ? h->s_photol.as<double>() + c0 : nullptr,
-                                    have_kh ? h->s_khet.as<double>() + c0 : nullptr, d_rc + c0, h->stream, ncell));
-      h->stats[6] += 1;
-    }
-    rc = run_integrator(h, d, ncell, (int)n, h->ident.as<int>() + c0, h->s_conc_in.as<double>(), d_rc,
-                        hstart ? h->s_hstart.as<double>() : nullptr, h->s_conc_out.as<double>(), h->s_ist.as<int32_t>(),
-                        h->s_rst.as<double>(), h->s_ierr.as<int32_t>());
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(ev_done[i], h->stream));
-    CUDA_TRY(cudaStreamWaitEvent(h->s_out, ev_done[i], 0));
-    CUDA_TRY(rows_out(conc_out, h->s_conc_out.p, c0, n, T->nspec, 8, h->s_out));
-    if (istatus) CUDA_TRY(rows_out(istatus, h->s_ist.p, c0, n, 8, 4, h->s_out));
-    if (rstatus) CUDA_TRY(rows_out(rstatus, h->s_rst.p, c0, n, 4, 8, h->s_out));
-    if (ierr) CUDA_TRY(rows_out(ierr, h->s_ierr.p, c0, n, 1, 4, h->s_out));
-  }
-  CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-  unsigned long long sums[64];
-  CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->s_out));
-  for (int i = 0; i < K; i++) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); }
-  float ms = 0;
-  cudaEventElapsedTime(&ms, h->ev[1], h->ev[3]); h->stats[0] = ms; h->stats[9] = ms;
-  h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1]; h->stats[5] = 0;
   return 0;
 }
+
+static void free_slots(gckpp_gpu_handle *h)
+{
+  if (!h->slots) return;
+  for (int i = 0; i < 2; i++) {
+    WaveSlot &s = h->slots[i];
+    DevBuf *b[] = {&s.conc_in, &s.conc_out, &s.rconst, &s.met, &s.photol, &s.khet, &s.hstart, &s.active, &s.ist, &s.rst, &s.ierr};
+    for (DevBuf *x : b) x->release();
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_out) cudaEventDestroy(s.ev_out);
+  }
+  delete[] h->slots;
+  h->slots = nullptr;
+}
+
+// "pin"=1: page-lock the caller's arrays for the duration of the call (Fortran State_Chm arrays are pageable; copies
+// from pageable memory are staged by the driver and do not overlap).  Registration failures are not errors.
+struct HostPins {
+  std::vector<void *> p;
+  void add(const void *ptr, size_t bytes)
+  {
+    if (ptr && bytes && cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) p.push_back(const_cast<void *>(ptr));
+    else cudaGetLastError();
+  }
+  ~HostPins() { for (void *q : p) cudaHostUnregister(q); }
+};
 
 extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin, double tout,
                                    const double *conc_in, const double *rconst,
@@ -813,52 +822,106 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
   CUDA_TRY(cudaSetDevice(h->device));
   const gckpp_host_tables_t *T = h->T;
   const size_t nc = (size_t)ncell;
-  int rc;
-  if (!active && !h->opt_retry && h->opt_chunks > 1 && ncell >= 4096 * h->opt_chunks && T->nnz > 0)
-    return integrate_pipelined(h, ncell, tin, tout, conc_in, rconst, temp, numden, h2o, photol, khet, atol, rtol, icntrl,
-                               rcntrl, hstart, conc_out, istatus, rstatus, ierr);
-  CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-  if ((rc = h2d(h, h->s_conc_in, conc_in, sizeof(double) * T->nspec * nc))) return rc;
-  if (rconst && (rc = h2d(h, h->s_rconst, rconst, sizeof(double) * T->nreact * nc))) return rc;
-  double *d_temp = nullptr, *d_numden = nullptr, *d_h2o = nullptr;
-  if (temp && numden && h2o) {
-    if (h->s_met.ensure(3 * sizeof(double) * nc)) return fail(-1002, "out of device memory");
-    d_temp = h->s_met.as<double>(); d_numden = d_temp + nc; d_h2o = d_numden + nc;
-    CUDA_TRY(cudaMemcpyAsync(d_temp, temp, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_numden, numden, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_h2o, h2o, sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
-  }
-  if (photol && T->nphot && (rc = h2d(h, h->s_photol, photol, sizeof(double) * T->nphot * nc))) return rc;
-  if (khet && T->next && (rc = h2d(h, h->s_khet, khet, sizeof(double) * T->next * nc))) return rc;
-  if (hstart && (rc = h2d(h, h->s_hstart, hstart, sizeof(double) * nc))) return rc;
-  if (active && (rc = h2d(h, h->s_active, active, nc))) return rc;
-  if (h->s_conc_out.ensure(sizeof(double) * T->nspec * nc) || h->s_ist.ensure(sizeof(int) * 8 * nc) ||
-      h->s_rst.ensure(sizeof(double) * 4 * nc) || h->s_ierr.ensure(sizeof(int) * nc))
-    return fail(-1002, "out of device memory");
-  CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
-  rc = gckpp_gpu_integrate_device(h, ncell, tin, tout, h->s_conc_in.as<double>(),
-                                  rconst ? h->s_rconst.as<double>() : nullptr, d_temp, d_numden, d_h2o,
-                                  (photol && T->nphot) ? h->s_photol.as<double>() : nullptr,
-                                  (khet && T->next) ? h->s_khet.as<double>() : nullptr, atol, rtol, icntrl, rcntrl,
-                                  hstart ? h->s_hstart.as<double>() : nullptr,
-                                  active ? h->s_active.as<uint8_t>() : nullptr, h->s_conc_out.as<double>(),
-                                  h->s_ist.as<int32_t>(), h->s_rst.as<double>(), h->s_ierr.as<int32_t>());
-  if (rc < 0) {
-    if (rc >= -5 && ierr) for (size_t i = 0; i < nc; i++) ierr[i] = rc;
+  Decoded d;
+  int rc = decode_options(T, tin, tout, icntrl, rcntrl, atol, rtol, d);
+  if (rc) {
+    if (ierr && rc >= -5) for (size_t i = 0; i < nc; i++) ierr[i] = rc;
     return rc;
   }
-  CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
-  CUDA_TRY(cudaMemcpyAsync(conc_out, h->s_conc_out.p, sizeof(double) * T->nspec * nc, cudaMemcpyDeviceToHost, h->stream));
-  if (istatus) CUDA_TRY(cudaMemcpyAsync(istatus, h->s_ist.p, sizeof(int) * 8 * nc, cudaMemcpyDeviceToHost, h->stream));
-  if (rstatus) CUDA_TRY(cudaMemcpyAsync(rstatus, h->s_rst.p, sizeof(double) * 4 * nc, cudaMemcpyDeviceToHost, h->stream));
-  if (ierr) CUDA_TRY(cudaMemcpyAsync(ierr, h->s_ierr.p, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  float a = 0, b = 0;
-  cudaEventElapsedTime(&a, h->ev[4], h->ev[5]);
-  cudaEventElapsedTime(&b, h->ev[6], h->ev[7]);
-  h->stats[2] = a + b;
-  return rc;
+  if ((rc = check_decoded(h, d))) return rc;
+  if (!rconst && (!temp || !numden || !h2o)) return fail(-10, "rconst is NULL and temp/numden/h2o are not all given");
+  if ((rc = ensure_slots(h))) return rc;
+  for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
+  const bool have_met = temp && numden && h2o, have_ph = photol && T->nphot, have_kh = khet && T->next;
+  // wave size: "wave_cells" (default 65536), or ncell / "chunks" when that option was set explicitly
+  size_t W = (size_t)(h->opt_wave_cells > 0 ? h->opt_wave_cells : 65536);
+  if (h->opt_chunks > 0) W = (nc + h->opt_chunks - 1) / h->opt_chunks;
+  if (W > nc) W = nc;
+  if (W < 1) W = 1;
+  const int nwaves = (int)((nc + W - 1) / W);
+  HostPins pins;
+  if (h->opt_pin) {
+    pins.add(conc_in, 8 * T->nspec * nc); pins.add(conc_out, 8 * T->nspec * nc);
+    if (rconst) pins.add(rconst, 8 * T->nreact * nc);
+    if (have_met) { pins.add(temp, 8 * nc); pins.add(numden, 8 * nc); pins.add(h2o, 8 * nc); }
+    if (have_ph) pins.add(photol, 8 * T->nphot * nc);
+    if (have_kh) pins.add(khet, 8 * T->next * nc);
+    if (hstart) pins.add(hstart, 8 * nc);
+    if (istatus) pins.add(istatus, 4 * 8 * nc);
+    if (rstatus) pins.add(rstatus, 8 * 4 * nc);
+    if (ierr) pins.add(ierr, 4 * nc);
+  }
+  for (int i = 0; i < 2 && i < nwaves; i++) {
+    WaveSlot &s = h->slots[i];
+    if (s.conc_in.ensure(8 * T->nspec * W) || s.conc_out.ensure(8 * T->nspec * W) || s.ist.ensure(4 * 8 * W) ||
+        s.rst.ensure(8 * 4 * W) || s.ierr.ensure(4 * W) || s.rconst.ensure(8 * T->nreact * W) ||
+        (have_met && s.met.ensure(3 * 8 * W)) || (hstart && s.hstart.ensure(8 * W)) || (active && s.active.ensure(W)) ||
+        (have_ph && s.photol.ensure(8 * T->nphot * W)) || (have_kh && s.khet.ensure(8 * T->next * W)))
+      return fail(-1002, "out of device memory for a wave of %zu cells", W);
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
+  // rows x n elements of a [rows][ncell] host array <-> a [rows][n] device array
+  auto rows_in = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt) {
+    return cudaMemcpy2DAsync(dst, n * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows, cudaMemcpyHostToDevice, h->s_in);
+  };
+  auto rows_out = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt) {
+    return cudaMemcpy2DAsync((char *)dst + c0 * elt, nc * elt, src, n * elt, n * elt, rows, cudaMemcpyDeviceToHost, h->s_out);
+  };
+  auto copy_in = [&](int w) -> int {
+    WaveSlot &s = h->slots[w & 1];
+    const size_t c0 = (size_t)w * W, n = (c0 + W <= nc) ? W : nc - c0;
+    if (w >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, s.ev_out, 0));      // the slot's previous results have left
+    CUDA_TRY(rows_in(s.conc_in.p, conc_in, c0, n, T->nspec, 8));
+    if (rconst) CUDA_TRY(rows_in(s.rconst.p, rconst, c0, n, T->nreact, 8));
+    if (have_met) {
+      double *m = s.met.as<double>();
+      CUDA_TRY(rows_in(m, temp, c0, n, 1, 8)); CUDA_TRY(rows_in(m + n, numden, c0, n, 1, 8)); CUDA_TRY(rows_in(m + 2 * n, h2o, c0, n, 1, 8));
+    }
+    if (have_ph) CUDA_TRY(rows_in(s.photol.p, photol, c0, n, T->nphot, 8));
+    if (have_kh) CUDA_TRY(rows_in(s.khet.p, khet, c0, n, T->next, 8));
+    if (hstart) CUDA_TRY(rows_in(s.hstart.p, hstart, c0, n, 1, 8));
+    if (active) CUDA_TRY(rows_in(s.active.p, active, c0, n, 1, 1));
+    CUDA_TRY(cudaEventRecord(s.ev_in, h->s_in));
+    return 0;
+  };
+  CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+  if ((rc = copy_in(0))) return rc;
+  unsigned long long fails = 0;
+  for (int w = 0; w < nwaves; w++) {
+    WaveSlot &s = h->slots[w & 1];
+    const size_t c0 = (size_t)w * W, n = (c0 + W <= nc) ? W : nc - c0;
+    if (w + 1 < nwaves && (rc = copy_in(w + 1))) return rc;               // runs ahead of the integration of wave w
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, s.ev_in, 0));
+    double *m = s.met.as<double>();
+    DevIO io{s.conc_in.as<double>(), rconst ? s.rconst.as<double>() : nullptr, have_met ? m : nullptr, have_met ? m + n : nullptr,
+             have_met ? m + 2 * n : nullptr, have_ph ? s.photol.as<double>() : nullptr, have_kh ? s.khet.as<double>() : nullptr,
+             hstart ? s.hstart.as<double>() : nullptr, active ? s.active.as<uint8_t>() : nullptr, s.conc_out.as<double>(),
+             s.ist.as<int32_t>(), s.rst.as<double>(), s.ierr.as<int32_t>(), s.rconst.as<double>()};
+    if ((rc = device_core(h, d, (int)n, io, &fails))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev_done, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, s.ev_done, 0));
+    CUDA_TRY(rows_out(conc_out, s.conc_out.p, c0, n, T->nspec, 8));
+    if (istatus) CUDA_TRY(rows_out(istatus, s.ist.p, c0, n, 8, 4));
+    if (rstatus) CUDA_TRY(rows_out(rstatus, s.rst.p, c0, n, 4, 8));
+    if (ierr) CUDA_TRY(rows_out(ierr, s.ierr.p, c0, n, 1, 4));
+    CUDA_TRY(cudaEventRecord(s.ev_out, h->s_out));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+  if ((rc = finish_stats(h))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->s_out));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[3]);
+  h->stats[0] = ms; h->stats[9] = ms; h->stats[11] = nwaves;
+  return h->opt_retry ? (int)h->stats[5] : 0;
+}
+
+static int h2d(gckpp_gpu_handle *h, DevBuf &b, const void *src, size_t bytes)
+{
+  if (b.ensure(bytes)) return fail(-1002, "out of device memory (%zu MB)", bytes >> 20);
+  CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
 }
 
 extern "C" int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *h, int ncell,

@@ -23,19 +23,20 @@ __device__ __forceinline__ MetCell make_met(double temp, double numden, double h
 }
 
 template <int MECH>
-__global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int stride, const double *__restrict__ temp,
+__global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int stride, int ostride, const double *__restrict__ temp,
     const double *__restrict__ numden, const double *__restrict__ h2o, const double *__restrict__ photol,
     const double *__restrict__ khet, double *__restrict__ rconst)
 {
-  // ncell cells starting at the given pointers; rows of the cell-fastest arrays are `stride` apart
+  // ncell cells starting at the given pointers; rows of the cell-fastest input arrays are `stride` apart, rows of
+  // rconst `ostride`
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= ncell) return;
   MetCell m = make_met(temp[cell], numden[cell], h2o[cell]);
   const double *ph = photol ? photol + cell : nullptr;
   const double *kh = khet ? khet + cell : nullptr;
-  if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
-  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
-  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride);
+  if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
+  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
+  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
 }
 
 __global__ void fill_int_kernel(int *p, int n, int v)
@@ -44,12 +45,13 @@ __global__ void fill_int_kernel(int *p, int n, int v)
   if (i < n) p[i] = v;
 }
 
-__global__ void select_active_kernel(int ncell, const uint8_t *__restrict__ active, int nspec,
+__global__ void select_active_kernel(int ncell, int c0, int c1, const uint8_t *__restrict__ active, int nspec,
     const double *__restrict__ conc_in, double *__restrict__ conc_out, int *istatus, double *rstatus,
     int *ierr, int *cell_list, int *count)
 {
-  int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  bool act = cell < ncell && active[cell] != 0;
+  // cells c0 <= cell < c1 of arrays with row stride ncell
+  int cell = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = cell < c1 && active[cell] != 0;
   unsigned mask = __ballot_sync(0xffffffffu, act);
   int lane = threadIdx.x & 31, base = 0;
   if (mask) {
@@ -58,7 +60,7 @@ __global__ void select_active_kernel(int ncell, const uint8_t *__restrict__ acti
     base = __shfl_sync(0xffffffffu, base, leader);
   }
   if (act) cell_list[base + __popc(mask & ((1u << lane) - 1u))] = cell;
-  if (cell < ncell && !act) {
+  if (cell < c1 && !act) {
     for (int s = 0; s < nspec; s++) conc_out[(size_t)s * ncell + cell] = conc_in[(size_t)s * ncell + cell];
     if (istatus) for (int q = 0; q < 8; q++) istatus[(size_t)q * ncell + cell] = 0;
     if (rstatus) for (int q = 0; q < 4; q++) rstatus[(size_t)q * ncell + cell] = 0.0;
@@ -66,10 +68,10 @@ __global__ void select_active_kernel(int ncell, const uint8_t *__restrict__ acti
   }
 }
 
-__global__ void select_failed_kernel(int ncell, const int *__restrict__ ierr, int *cell_list, int *count)
+__global__ void select_failed_kernel(int c0, int c1, const int *__restrict__ ierr, int *cell_list, int *count)
 {
-  int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell < ncell && ierr[cell] < 0) cell_list[atomicAdd(count, 1)] = cell;
+  int cell = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell < c1 && ierr[cell] < 0) cell_list[atomicAdd(count, 1)] = cell;
 }
 
 // FP64 FMA peak: 8 independent DFMA chains per thread, 4096 iterations, 8 CTAs of 256 per SM.
@@ -119,13 +121,14 @@ cudaError_t measure_fp64_peak(double *tflops, double *ms_out)
 
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,
-                                 double *rconst, cudaStream_t s, int stride)
+                                 double *rconst, cudaStream_t s, int stride, int ostride)
 {
   int blocks = (ncell + 127) / 128;
   if (stride <= 0) stride = ncell;
-  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
-  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
-  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, temp, numden, h2o, photol, khet, rconst);
+  if (ostride <= 0) ostride = stride;
+  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
+  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
+  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
   return cudaGetLastError();
 }
 __global__ void iota_kernel(int *p, int n)
@@ -143,16 +146,16 @@ cudaError_t launch_fill_int(int *p, int n, int v, cudaStream_t s)
   fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n, v);
   return cudaGetLastError();
 }
-cudaError_t launch_select_active(int ncell, const uint8_t *active, int nspec, const double *conc_in,
+cudaError_t launch_select_active(int ncell, int c0, int c1, const uint8_t *active, int nspec, const double *conc_in,
                                  double *conc_out, int *istatus, double *rstatus, int *ierr,
                                  int *cell_list, int *count, cudaStream_t s)
 {
-  select_active_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(ncell, active, nspec, conc_in, conc_out, istatus,
-                                                           rstatus, ierr, cell_list, count);
+  select_active_kernel<<<(c1 - c0 + 255) / 256, 256, 0, s>>>(ncell, c0, c1, active, nspec, conc_in, conc_out, istatus,
+                                                             rstatus, ierr, cell_list, count);
   return cudaGetLastError();
 }
-cudaError_t launch_select_failed(int ncell, const int *ierr, int *cell_list, int *count, cudaStream_t s)
+cudaError_t launch_select_failed(int c0, int c1, const int *ierr, int *cell_list, int *count, cudaStream_t s)
 {
-  select_failed_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(ncell, ierr, cell_list, count);
+  select_failed_kernel<<<(c1 - c0 + 255) / 256, 256, 0, s>>>(c0, c1, ierr, cell_list, count);
   return cudaGetLastError();
 }

@@ -38,6 +38,7 @@ struct RosArgs {
   int nwork;                   // cells to integrate in this launch
   const int *cell_list;        // [nwork] cell indices, or NULL for 0..nwork-1
   const double *conc_in, *rconst, *hstart, *atol, *rtol;
+  int rc_stride, rc_cell0;     // rconst is [NREACT][rc_stride] and its column 0 is cell rc_cell0 (a wave's own rate constants)
   double *conc_out;
   int *istatus;                // [8][ncell] or NULL
   double *rstatus;             // [4][ncell] or NULL

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) ros_generic_kernel(MechDev M, RosArgs a)
             Y[(size_t)s * st] = v;
             if (s >= N) YN[(size_t)s * st] = v;      // fixed species ride along in both state vectors
           }
-          for (int r = 0; r < M.nreact; r++) RC[(size_t)r * st] = a.rconst[(size_t)r * a.ncell + cell];
+          for (int r = 0; r < M.nreact; r++) RC[(size_t)r * st] = a.rconst[(size_t)r * a.rc_stride + (cell - a.rc_cell0)];
 #pragma unroll
           for (int q = 0; q < 8; q++) ist[q] = 0;
           // Integrate's merge (RCNTRL_U > 0 overrides) and Rosenbrock's Hstart rule (:420-428)
@@ -397,16 +397,22 @@ __global__ void feuler_kernel(MechDev M, RosArgs a, int icntrl16)
   int cell = a.cell_list ? a.cell_list[w] : w;
   double y[FE_MAX], rc[FE_MAX], A[FE_MAX], vd[FE_MAX];
   for (int s = 0; s < M.nspec; s++) y[s] = a.conc_in[(size_t)s * a.ncell + cell];
-  for (int r = 0; r < M.nreact; r++) rc[r] = a.rconst[(size_t)r * a.ncell + cell];
+  for (int r = 0; r < M.nreact; r++) rc[r] = a.rconst[(size_t)r * a.rc_stride + (cell - a.rc_cell0)];
   g_fun(M, y, rc, A, vd, 1);
+  // KPP/carbon/gckpp_Integrator.F90:187-211: a negative entry is clipped (ICNTRL(16) = 1) or makes the routine
+  // return IERR = -9 with Y untouched (= 2; = 3 STOPs in the reference, reported the same way here)
   int ierr = 1;
+  bool early = false;
   double dt = a.o.Tend - a.o.Tstart;
-  for (int i = 0; i < M.nvar; i++) {
-    double v = y[i] + vd[i] * dt;
-    if (icntrl16 == 1 && v < 0.0) v = 0.0;
-    if (icntrl16 == 2 && v < 0.0) ierr = -1;
-    y[i] = v;
-  }
+  for (int i = 0; i < M.nvar; i++) vd[i] = y[i] + vd[i] * dt;
+  if (icntrl16 > 0)
+    for (int i = 0; i < M.nvar && !early; i++)
+      if (vd[i] < 0.0) {
+        if (icntrl16 == 1) vd[i] = 0.0;
+        else if (icntrl16 == 2 || icntrl16 == 3) early = true;
+      }
+  if (early) ierr = -9;
+  else for (int i = 0; i < M.nvar; i++) y[i] = vd[i];
   for (int s = 0; s < M.nspec; s++) a.conc_out[(size_t)s * a.ncell + cell] = y[s];
   if (a.istatus) {
     for (int q = 0; q < 8; q++) a.istatus[(size_t)q * a.ncell + cell] = 0;

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           const int r = k * NT + tid;
           if (r < M::NREACT) {
             const int i0 = awt[r].x & 0xffff;
-            rcsA[(c * NA_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - M::NREACT];
+            rcsA[(c * NA_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.rc_stride + (ic - a.rc_cell0)] : P.lit[i0 - M::NREACT];
           }
         }
 #pragma unroll
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           const int m = k * NT + tid;
           if (m < M::NB) {
             const int i0 = bwt[m].x & 0xffff;
-            rcsB[(c * NB_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + ic] : P.lit[i0 - M::NREACT];
+            rcsB[(c * NB_IT + k) * NT + tid] = i0 < M::NREACT ? a.rconst[(size_t)i0 * a.rc_stride + (ic - a.rc_cell0)] : P.lit[i0 - M::NREACT];
           }
         }
       } else if (!slot[c].have) {

@@ -100,7 +100,10 @@ struct WLay {
   static constexpr int gSCR = gX + a128((XPAD + 1) * 8);   // X[0..63] doubles as the pivot-row buffer of tail_lu
   static constexpr int gCTL = gSCR + a128(cmax(NSCR * 8, 16 * 32 * 8));   // SCR doubles as the L panel of tail_lu
   static constexpr int GSZ = gCTL + a128((int)sizeof(GCtl));
-  static constexpr int NGRP = cmin(cmin(1024 / GT, WG == 1 ? 16 : 15), (SMEM_LIMIT - oGRP) / GSZ);
+#ifndef WARP_MAXG
+#define WARP_MAXG 15
+#endif
+  static constexpr int NGRP = cmin(cmin(1024 / GT, WG == 1 ? 16 : WARP_MAXG), (SMEM_LIMIT - oGRP) / GSZ);
   static constexpr int TOTAL = oGRP + NGRP * GSZ;
   static constexpr int NQ = (M::NSPEC + GT - 1) / GT;
 };
@@ -214,12 +217,17 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c
     } else {                            // three table rows, and a loop for the rare longer lane
       const uint4 r1 = rd.w1, r2 = rd.w2;
       rd.advance3();
-      LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2); LDT(r1.y, h3, l3); LDT(r1.z, h4, l4); LDT(r1.w, h5, l5);
-      LDT(r2.x, h6, l6);
-      LDP(T > 7, r2.y, h7, l7) LDP(T > 8, r2.z, h8, l8) LDP(T > 9, r2.w, h9, l9)
-      a0 = h0 * l0; a1 = h1 * l1; a2 = h2 * l2; a3 = h3 * l3;
-      a0 = fma(h4, l4, a0); a1 = fma(h5, l5, a1); a2 = fma(h6, l6, a2); a3 = fma(h7, l7, a3);
-      a0 = fma(h8, l8, a0); a1 = fma(h9, l9, a1);
+      {
+        LDT(r0.z, h0, l0); LDT(r0.w, h1, l1); LDT(r1.x, h2, l2); LDT(r1.y, h3, l3); LDT(r1.z, h4, l4); LDT(r1.w, h5, l5);
+        a0 = h0 * l0; a1 = h1 * l1; a2 = h2 * l2; a3 = h3 * l3;
+        a0 = fma(h4, l4, a0); a1 = fma(h5, l5, a1);
+      }
+      {
+        LDT(r2.x, h6, l6);
+        LDP(T > 7, r2.y, h7, l7) LDP(T > 8, r2.z, h8, l8) LDP(T > 9, r2.w, h9, l9)
+        a2 = fma(h6, l6, a2); a3 = fma(h7, l7, a3);
+        a0 = fma(h8, l8, a0); a1 = fma(h9, l9, a1);
+      }
 #pragma unroll 1
       for (int k = 10; k < T; k += 4) {
         const uint4 r3 = rd.w0;
@@ -270,8 +278,11 @@ __device__ __forceinline__ void run_phase(WReader &rd, int nb, int nlev, WCtx &c
 // as its entry has been updated.  Entries outside the LU pattern are exact zeros and stay zero (fill-in closure).
 // The factors are stored in their final form: L multipliers, the reciprocal diagonal, and U entries scaled by the
 // reciprocal diagonal of their row.
+#ifndef WARP_TAIL_INLINE
+#define WARP_TAIL_INLINE __forceinline__
+#endif
 template <class M>
-__device__ __forceinline__ bool tail_lu(double *Gc, double *buf /* 2 x 16 */, double *lpan /* 16 x 32 */, const uint16_t *tposT, int lane)
+__device__ WARP_TAIL_INLINE bool tail_lu(double *Gc, double *buf /* 2 x 16 */, double *lpan /* 16 x 32 */, const uint16_t *tposT, int lane)
 {
   constexpr int m = M::TAIL, hp = 16;
   static_assert(m == 2 * hp, "two panels of 16 columns");
@@ -361,7 +372,7 @@ __device__ __forceinline__ bool tail_lu(double *Gc, double *buf /* 2 x 16 */, do
 // the tail rows of one solve: forward chain x_i -= L(i,j) x_j (j ascending), scaling by the reciprocal
 // pivot, backward chain x_i -= U'(i,j) x_j (j descending); x stays in a register per lane
 template <class M>
-__device__ __forceinline__ void tail_solve(const double *Gc, double *Xc, const uint16_t *tposT, const uint16_t *diag, int lane)
+__device__ WARP_TAIL_INLINE void tail_solve(const double *Gc, double *Xc, const uint16_t *tposT, const uint16_t *diag, int lane)
 {
   constexpr int m = M::TAIL;
   double x = (lane < m) ? Xc[M::HEAD + lane] : 0.0;
@@ -525,12 +536,12 @@ __global__ void __launch_bounds__(WLay<M>::NGRP * WLay<M>::GT, 1) ros_warp_kerne
 #pragma unroll 4
     for (int r = gtid; r < M::NREACT; r += GT) {
       const int i0 = __ldg(awt + r).x & 0xffff;
-      __stcg(rcsA + r, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + cell] : P.lit[i0 - M::NREACT]);
+      __stcg(rcsA + r, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.rc_stride + (cell - a.rc_cell0)] : P.lit[i0 - M::NREACT]);
     }
 #pragma unroll 4
     for (int m = gtid; m < M::NB; m += GT) {
       const int i0 = __ldg(bwt + m).x & 0xffff;
-      __stcg(rcsB + m, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.ncell + cell] : P.lit[i0 - M::NREACT]);
+      __stcg(rcsB + m, i0 < M::NREACT ? a.rconst[(size_t)i0 * a.rc_stride + (cell - a.rc_cell0)] : P.lit[i0 - M::NREACT]);
     }
     gsync<WG>(group);
 

@@ -162,6 +162,29 @@ def make_grid(name="4x5", hstart="warm", rank=0, world=1, seed=SEED, limit=None)
     return g
 
 
+def make_small_mech(mech, cells, seed=SEED):
+    """Config 5: inputs of the carbon and Hg mechanisms for the given cells.  The reference ships no sample for
+    them, so concentrations and rate constants are log-uniform in ranges that keep the systems stiff but
+    integrable (documented here, shard-invariant like make_cells):
+      Hg      C0 in 1e2..1e8 molec/cm3, RCONST in 1e-16..1e-11, one 3600 s step, RTOL 1e-2 (mercury_mod.F90:951-1167)
+      carbon  C0 in 1e4..1e12 molec/cm3, RCONST in 1e-16..1e-9, one 3600 s forward-Euler step"""
+    from .kppgen import ir
+    m = ir.load(mech)
+    cells = np.asarray(cells, dtype=np.int64)
+    n = cells.shape[0]
+    lo_c, hi_c, lo_r, hi_r = (2.0, 8.0, -16.0, -11.0) if mech == "Hg" else (4.0, 12.0, -16.0, -9.0)
+    conc = np.empty((m.nspec, n))
+    for s in range(m.nspec):
+        conc[s] = 10.0 ** (lo_c + (hi_c - lo_c) * _hash_u01(seed, cells, s, 61))
+    rconst = np.empty((m.nreact, n))
+    for r in range(m.nreact):
+        rconst[r] = 10.0 ** (lo_r + (hi_r - lo_r) * _hash_u01(seed, cells, r, 71))
+    icntrl = np.zeros(20, np.int32)
+    icntrl[0], icntrl[2], icntrl[6], icntrl[14] = 1, 4, 1, -1
+    return dict(conc=conc, rconst=rconst, atol=np.full(m.nvar, 1e-2), rtol=np.full(m.nvar, 1e-2), icntrl=icntrl,
+                rcntrl=np.zeros(20), cells=cells, dt=3600.0)
+
+
 def replicate_fixture(n, fx=None):
     """Config 1: the fixture cell replicated n times (zero divergence)."""
     fx = fx or load_fixture()

@@ -154,6 +154,7 @@ class KppSolver:
         if rc != 0:
             raise KppError("gckpp_gpu_init failed (%d): %s" % (rc, self.L.gckpp_gpu_last_error().decode()))
         self.h = h
+        self._user_stream = False
         if retry:
             self.set_option("retry", 1)
 
@@ -178,8 +179,24 @@ class KppSolver:
             raise KppError(self.L.gckpp_gpu_last_error().decode())
 
     def set_stream(self, cuda_stream_ptr):
-        """run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream"""
+        """run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = the default:
+        torch tensors run on torch's current stream, host arrays on the handle's own stream"""
+        self._user_stream = bool(cuda_stream_ptr)
         self.L.gckpp_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None)
+
+    def _torch_stream(self, *tensors):
+        """device entry points: every array must be a CUDA tensor of this device, and the work is ordered after the
+        kernels that produced them -- it runs on torch's current stream unless set_stream() chose one"""
+        import torch
+        for t in tensors:
+            if t is None:
+                continue
+            if not _is_torch(t) or not t.is_cuda or t.device.index != self.device:
+                raise ValueError("device entry point: every array must be a CUDA tensor on cuda:%d" % self.device)
+            if not t.is_contiguous():
+                raise ValueError("device entry point: tensors must be contiguous")
+        if not self._user_stream:
+            self.L.gckpp_gpu_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
 
     def _check(self, rc, what):
         if rc < 0:
@@ -196,6 +213,7 @@ class KppSolver:
             ncell = TEMP.shape[0]
             if out is None:
                 out = torch.empty((d["nreact"], ncell), dtype=torch.float64, device=TEMP.device)
+            self._torch_stream(TEMP, NUMDEN, H2O, PHOTOL, khet, out)
             rc = self.L.gckpp_gpu_update_rconst_device(self.h, ncell, _ptr(TEMP), _ptr(NUMDEN), _ptr(H2O),
                                                        _ptr(PHOTOL), _ptr(khet), _ptr(out))
             self._check(rc, "Update_RCONST")
@@ -237,6 +255,7 @@ class KppSolver:
                 RSTATUS = torch.empty((4, ncell), dtype=torch.float64, device=dev)
             if IERR is None:
                 IERR = torch.empty((ncell,), dtype=torch.int32, device=dev)
+            self._torch_stream(C_in, RCONST, TEMP, NUMDEN, H2O, PHOTOL, khet, hstart, active, C_out, ISTATUS, RSTATUS, IERR)
             fn = self.L.gckpp_gpu_integrate_device
         else:
             C_in = _np(C_in, np.float64)
@@ -303,7 +322,7 @@ class KppSolver:
         s = (C.c_double * 16)()
         self.L.gckpp_gpu_last_stats(self.h, s)
         keys = ("integrate_ms", "rconst_ms", "copy_ms", "cells", "retried", "failed_twice", "launches", "sum_nstp",
-                "sum_nacc", "device_ms")
+                "sum_nacc", "device_ms", "failed_integrations", "waves")
         return dict(zip(keys, (float(x) for x in s)))
 
 

@@ -255,9 +255,9 @@ static int ros_integrator(ros_ctx_t *c, const ros_method_t *ros, double *Y, doub
   const kpp_mech_t *m = c->m;
   const int N = m->nvar, S = ros->S;
   const double DeltaMin = 1.0E-5;
-  double *Ynew = malloc(sizeof(double) * (size_t)N * (5 + S));
+  double Ynew[(size_t)N * (5 + S)];            /* work arrays on the stack, like the reference's automatic arrays (:590-600) */
   double *Fcn0 = Ynew + N, *Fcn = Fcn0 + N, *dFdT = Fcn + N, *Yerr = dFdT + N, *K = Yerr + N;
-  double *Jac0 = malloc(sizeof(double) * (size_t)m->lu_nonzero * 2);
+  double Jac0[(size_t)m->lu_nonzero * 2];
   double *Ghimj = Jac0 + m->lu_nonzero;
   double T, H, Hnew, HC, HG, Fac, Tau, Err;
   int Direction, j, istage, i, IERR = 0;
@@ -374,27 +374,31 @@ static int ros_integrator(ros_ctx_t *c, const ros_method_t *ros, double *Y, doub
   IERR = 1;
 done:
   *Tout = T;
-  free(Ynew);
-  free(Jac0);
   return IERR;
 }
 
-/* forward Euler "integrator" of the carbon mechanism (KPP/carbon/gckpp_Integrator.F90:155-215):
- * one explicit step over the whole interval; ICNTRL(16) selects the negativity handling
- * (0 nothing, 1 clip to zero, 2 report error -1 on any negative) */
+/* forward Euler "integrator" of the carbon mechanism (KPP/carbon/gckpp_Integrator.F90:155-215), literally:
+ * Ynew = Y + dYdt*(Tend-Tstart); if ICNTRL(16) > 0 the entries are scanned in order and a negative one sets
+ * IERR = -9 and is clipped (ICNTRL(16) = 1) or makes the routine RETURN with Y untouched (= 2; = 3 would STOP,
+ * reported the same way here); otherwise Y = Ynew and IERR = 1 (which also overwrites the -9 of the clip case). */
 static int feuler_integrator(ros_ctx_t *c, double *Y, double Tstart, double Tend, int icntrl16)
 {
   const int N = c->m->nvar;
-  double *dYdt = malloc(sizeof(double) * N);
-  int i, ierr = 1;
+  double *dYdt = malloc(sizeof(double) * N), *Ynew = malloc(sizeof(double) * N);
+  int i, ierr = 1, early = 0;
   fun_template(c, Y, dYdt);
   c->ISTATUS[Nfun]++;
-  for (i = 0; i < N; i++) Y[i] = Y[i] + dYdt[i] * (Tend - Tstart);
-  if (icntrl16 == 1) {
-    for (i = 0; i < N; i++) if (Y[i] < 0.0) Y[i] = 0.0;
-  } else if (icntrl16 == 2) {
-    for (i = 0; i < N; i++) if (Y[i] < 0.0) ierr = -1;
+  for (i = 0; i < N; i++) Ynew[i] = Y[i] + dYdt[i] * (Tend - Tstart);
+  if (icntrl16 > 0) {
+    for (i = 0; i < N && !early; i++)
+      if (Ynew[i] < 0.0) {
+        if (icntrl16 == 1) Ynew[i] = 0.0;
+        else if (icntrl16 == 2 || icntrl16 == 3) early = 1;
+      }
   }
+  if (early) ierr = -9;
+  else for (i = 0; i < N; i++) Y[i] = Ynew[i];
+  free(Ynew);
   c->ISTATUS[Nstp]++;
   c->ISTATUS[Nacc]++;
   c->RSTATUS[Ntexit] = Tend;
@@ -426,7 +430,7 @@ int kpp_oracle_integrate_cell(int mech_id, double tin, double tout, double *C, c
    * call Update_SUN/Update_RCONST inside Fun/Jac, which needs the host's met state. */
   if (ICNTRL[14] != -1) return -101;
 
-  double *scratch = malloc(sizeof(double) * ((size_t)m->nreact + 3 * (size_t)m->nvar + (size_t)m->nb + 8));
+  double scratch[(size_t)m->nreact + 3 * (size_t)m->nvar + (size_t)m->nb + 8];
   ctx.m = m;
   ctx.RCONST = RCONST;
   ctx.FIX = C + m->nvar;
@@ -440,7 +444,6 @@ int kpp_oracle_integrate_cell(int mech_id, double tin, double tout, double *C, c
 
   if (!m->jac_sp) { /* carbon: forward Euler */
     IERR = feuler_integrator(&ctx, C, tin, tout, ICNTRL[15]);
-    free(scratch);
     return IERR;
   }
 
@@ -504,7 +507,6 @@ int kpp_oracle_integrate_cell(int mech_id, double tin, double tout, double *C, c
     }
   }
 out:
-  free(scratch);
   return IERR;
 }
 

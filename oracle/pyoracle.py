@@ -15,16 +15,44 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
+LIBS = {"strict": "libkpp_oracle.so", "fma": "libkpp_oracle_fma.so", "native": "libkpp_oracle_native.so"}
+
+
 def build(variant="strict"):
-    target = "libkpp_oracle.so" if variant == "strict" else "libkpp_oracle_fma.so"
+    """strict: -O2 -march=x86-64-v3 (travels to the GPU box); native: -O3 -march=native, built on the machine that
+    runs it (the CPU-baseline arm of bench.py); both without FMA contraction"""
+    target = LIBS[variant]
     subprocess.check_call(["make", "-C", HERE, "-j8", target], stdout=subprocess.DEVNULL)
     return os.path.join(HERE, target)
 
 
+def native_is_stale():
+    """the native build must come from this machine's compiler run (never shipped): rebuild when its CPU differs"""
+    tag = os.path.join(HERE, "build", "native", "cpu.txt")
+    try:
+        cpu = [l for l in open("/proc/cpuinfo") if l.startswith("model name")][0].strip()
+    except Exception:
+        cpu = "unknown"
+    lib = os.path.join(HERE, LIBS["native"])
+    if os.path.exists(lib) and os.path.exists(tag) and open(tag).read() == cpu:
+        return False, tag, cpu
+    return True, tag, cpu
+
+
 class Oracle:
     def __init__(self, variant="strict", autobuild=True):
-        name = "libkpp_oracle.so" if variant == "strict" else "libkpp_oracle_fma.so"
-        path = os.path.join(HERE, name)
+        self.variant = variant
+        if variant == "native":
+            stale, tag, cpu = native_is_stale()
+            if stale:
+                try:
+                    subprocess.call(["rm", "-rf", os.path.join(HERE, "build", "native"), os.path.join(HERE, LIBS["native"])])
+                    build("native")
+                    with open(tag, "w") as f:
+                        f.write(cpu)
+                except Exception:
+                    self.variant = variant = "strict"       # no compiler: fall back to the shipped strict build
+        path = os.path.join(HERE, LIBS[variant])
         if not os.path.exists(path):
             if not autobuild:
                 raise FileNotFoundError(path)

@@ -1,14 +1,15 @@
 """GPU parity tests proper: every call goes through the C ABI (libgckpp_b200.so) and is compared
-with the CPU oracle on the same inputs.  Two integrator kernels are covered: "smem" (the default,
-shared-memory-resident Rodas3 kernel; re-associated sums + FMA) and "table" (option kernel=0, the
-table-driven kernel in the reference's operation order).  Tolerances:
+with the CPU oracle on the same inputs.  Three integrator kernels are covered: "warp" (the default: one group
+of warps per cell, shared-memory-resident Rodas3, re-associated sums + FMA), "smem" (option kernel=1, round 1's
+block-synchronous shared-memory kernel) and "table" (option kernel=0, the table-driven kernel in the reference's
+operation order).  Tolerances:
   * single routines (Fun, Jac_SP, KppDecomp, KppSolve) with the table-driven kernel: bit-exact
     (same operation order, no FMA contraction; integer/IEEE +,-,*,/ only)
   * Update_RCONST: relative 1e-10 worst case, 1e-15 median (CUDA vs glibc exp/pow/log10 differ in
     the last ulps and some laws cancel)
   * Integrate: north-star bar -- every species above 1e3 molec/cm3 within 1e-4 relative (both
     kernels); step counts per cell identical for the table kernel, and reported (allowed to differ in
-    at most 0.1 % of the cells, each still within the 1e-4 bar) for the smem kernel
+    at most 0.1 % of the cells, each still within the 1e-4 bar) for the warp and smem kernels
 """
 import numpy as np
 import pytest
@@ -76,14 +77,14 @@ def test_update_rconst_vs_oracle(solver, oracle):
     assert np.median(err[ro != 0]) < 1e-15
 
 
-KERNELS = {"smem": 1, "table": 0}
+KERNELS = {"warp": 2, "smem": 1, "table": 0}
 
 
-@pytest.mark.parametrize("kernel", ["smem", "table"])
+@pytest.mark.parametrize("kernel", ["warp", "smem", "table"])
 def test_integrate_fixture_replicated(solver, fx, kernel):
     """config 1: the Beijing cell, replicated; the 3-D model's own answer is 12 steps, Hexit 497.8023"""
     solver.set_option("kernel", KERNELS[kernel])
-    r = grid.replicate_fixture(97, fx)     # odd count: the last block of the smem kernel runs half empty
+    r = grid.replicate_fixture(97, fx)     # odd count: the last block runs partly empty
     c, ist, rst, ierr, nf = solver.Integrate(0.0, r["dt"], r["conc"], r["rconst"], r["atol"], r["rtol"],
                                              r["icntrl"], r["rcntrl"])
     assert (ierr == 1).all()
@@ -100,7 +101,7 @@ def _parity(c, co, floor=1e3):
     return rel
 
 
-@pytest.mark.parametrize("kernel", ["smem", "table"])
+@pytest.mark.parametrize("kernel", ["warp", "smem", "table"])
 @pytest.mark.parametrize("hstart", ["warm", "cold"])
 def test_integrate_grid_sample_vs_oracle(solver, oracle, hstart, kernel):
     solver.set_option("kernel", KERNELS[kernel])
@@ -165,7 +166,7 @@ def test_hg_mechanism_vs_oracle(lib, oracle):
     icntrl = np.zeros(20, np.int32); icntrl[[0, 2, 6, 14]] = [1, 4, 1, -1]
     rcntrl = np.zeros(20)
     co, isto, rsto, ierro = oracle.integrate("Hg", 0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
-    for kernel in ("smem", "table"):
+    for kernel in ("warp", "smem", "table"):
         s.set_option("kernel", KERNELS[kernel])
         c, ist, rst, ierr, _ = s.Integrate(0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
         assert np.array_equal(ierr, ierro)
@@ -188,7 +189,7 @@ def test_standalone_box_model_cli(tmp_path, fx, capsys):
     p = tmp_path / "Beijing_L1_20190701_0040.txt"
     p.write_text(sample.format_sample(s))
     out = tmp_path / "out.txt"
-    for kernel in (1, 0):
+    for kernel in (2, 1, 0):
         rc = standalone.main([str(p), str(out), "--kernel", str(kernel)])
         txt = capsys.readouterr().out
         assert rc == 0, txt
@@ -252,7 +253,7 @@ def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method):
                               np.ascontiguousarray(g["photol"][:, idx]), np.ascontiguousarray(g["khet"][:, idx]))
     icntrl = g["icntrl"].copy()
     icntrl[2] = method
-    solver.set_option("kernel", 1)       # the default choice; the library itself must fall back
+    solver.set_option("kernel", -1)      # the default choice; the library itself must fall back
     co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
     c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
     assert np.array_equal(ierr, ierro)
@@ -282,7 +283,7 @@ def test_pipelined_host_entry_matches_serial(solver):
     assert (e1 == 1).all()
 
 
-@pytest.mark.parametrize("kernel", ["smem", "table"])
+@pytest.mark.parametrize("kernel", ["warp", "smem", "table"])
 @pytest.mark.parametrize("variant", ["non_autonomous", "scalar_tol", "clip_negative", "hmax_facmax"])
 def test_integrate_option_variants(solver, oracle, kernel, variant):
     """the rest of the option surface Rosenbrock() decodes (gckpp_Integrator.F90:345-467): ICNTRL(1)=0 (the time

@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 import torch
 from geos_chem_b200 import grid, kpp
 mode = sys.argv[1] if len(sys.argv) > 1 else "own"
-g = grid.make_grid("4x5", hstart="warm")
+g = grid.make_grid("4x5", hstart="warm", limit=int(os.environ.get("VB_CELLS", "0")) or None)
 n = g["conc"].shape[1]
 s = kpp.KppSolver("fullchem", 0, max_cells=n)
 for kv in sys.argv[2:]:
