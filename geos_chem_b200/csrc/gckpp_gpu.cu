@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "ros_smem.h"
 #include "ros_warp.h"
+#include "ros_lane.h"
 
 #include "gen/fullchem_tables.h"
 #include "gen/Hg_tables.h"
@@ -24,6 +25,8 @@
 #include "gen/Hg_sched.h"
 #include "gen/fullchem_wsched.h"
 #include "gen/Hg_wsched.h"
+#include "gen/fullchem_lsched.h"
+#include "gen/Hg_lsched.h"
 #include "gen/fullchem_names.h"
 #include "gen/Hg_names.h"
 #include "gen/carbon_names.h"
@@ -74,6 +77,15 @@ static const gckpp_wsched_tables_t *host_wsched(int mech_id)
   }
 }
 
+static const gckpp_lsched_tables_t *host_lsched(int mech_id)
+{
+  switch (mech_id) {
+  case GCKPP_MECH_FULLCHEM: return &fullchem_lsched;
+  case GCKPP_MECH_HG: return &Hg_lsched;
+  default: return nullptr;
+  }
+}
+
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
@@ -120,6 +132,10 @@ struct gckpp_gpu_handle {
   WarpHostPlan wplan;
   WarpArgs wargs{};
   DevBuf w_stream, w_aw, w_bw, w_diag, w_tpos, w_coefs, w_rcs;
+  // lane kernel: device copies of its stream tables, workspace of the resident blocks
+  int l_ready = 0, l_blocks = 0;
+  LaneArgs largs{};
+  DevBuf l_tab[7], l_lit, l_ws;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -237,6 +253,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->s_conc_in, &h->s_conc_out, &h->s_rconst, &h->s_met, &h->s_photol, &h->s_khet, &h->s_hstart,
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
                     &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
+                    &h->l_tab[0], &h->l_tab[1], &h->l_tab[2], &h->l_tab[3], &h->l_tab[4], &h->l_tab[5], &h->l_tab[6], &h->l_lit, &h->l_ws,
                     &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   free_slots(h);
@@ -521,11 +538,57 @@ static int prepare_warp(gckpp_gpu_handle *h)
 // Which integrator kernel serves this call: 2 = warp-per-cell (default for Rodas3, ICNTRL(3) = 0 or 4, the
 // method GEOS-Chem selects), 1 = the block-synchronous shared-memory kernel of round 1 (kept for comparison),
 // 0 = the table-driven reference-order kernel (every method, auto-reduce).
+// Upload the stream tables of the lane kernel once per handle and size its workspace: one warp per block, as many
+// blocks per SM as its shared memory (the VEC of 32 cells + the rings) allows.
+static int prepare_lane(gckpp_gpu_handle *h)
+{
+  if (h->l_ready) return 0;
+  const gckpp_lsched_tables_t *S = host_lsched(h->mech_id);
+  if (!S) return fail(-11, "lane kernel not available for this mechanism");
+  int maxsm = 0, smsm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&smsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+  const size_t smem = lane_smem_bytes(S->d);
+  if ((size_t)maxsm < smem) return fail(-11, "lane kernel needs %zu bytes of shared memory, device offers %d", smem, maxsm);
+  int bps = (int)((size_t)smsm / (smem + 1024));
+  if (bps < 1) bps = 1;
+  if (bps > 16) bps = 16;
+  LaneArgs &A = h->largs;
+  A.d = S->d;
+  const uint32_t *src[7] = {S->rates_a, S->sums_v, S->rates_b, S->sums_j, S->lu, S->fwd, S->bwd};
+  const int nch[7] = {S->nchunk_ra, S->nchunk_sv, S->nchunk_rb, S->nchunk_sj, S->nchunk_lu, S->nchunk_fwd, S->nchunk_bwd};
+  const int recq[7] = {2, 4, 2, 4, 2, 2, 2};
+  for (int i = 0; i < 7; i++) {
+    const size_t chunk = (size_t)16 * recq[i] * 16, bytes = (size_t)nch[i] * chunk;     // + one chunk of zero records
+    if (h->l_tab[i].ensure(bytes + chunk)) return fail(-1002, "out of device memory for the kernel tables");
+    CUDA_TRY(cudaMemcpy(h->l_tab[i].p, src[i], bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset((char *)h->l_tab[i].p + bytes, 0, chunk));
+  }
+  if (h->l_lit.ensure(sizeof(double) * (S->d.nlit > 0 ? S->d.nlit : 1))) return fail(-1002, "out of device memory");
+  if (S->d.nlit) CUDA_TRY(cudaMemcpy(h->l_lit.p, S->lit, sizeof(double) * S->d.nlit, cudaMemcpyHostToDevice));
+  A.rates_a = h->l_tab[0].as<uint4>(); A.sums_v = h->l_tab[1].as<uint4>(); A.rates_b = h->l_tab[2].as<uint4>();
+  A.sums_j = h->l_tab[3].as<uint4>(); A.lu = h->l_tab[4].as<uint4>(); A.fwd = h->l_tab[5].as<uint4>(); A.bwd = h->l_tab[6].as<uint4>();
+  A.nchunk_ra = nch[0]; A.nchunk_sv = nch[1]; A.nchunk_rb = nch[2]; A.nchunk_sj = nch[3]; A.nchunk_lu = nch[4];
+  A.nchunk_fwd = nch[5]; A.nchunk_bwd = nch[6];
+  A.lit = h->l_lit.as<double>();
+  const LaneDims &d = S->d;
+  int o = 0;
+  A.oY = o; o += d.nspec; A.oYN = o; o += d.nvar; A.oF0 = o; o += d.nvar; A.oFC = o; o += d.nvar;
+  A.oK = o; o += 6 * d.nvar; A.oGA = o; o += d.ng; A.oRCX = o; o += d.nrcx; A.oAB = o; o += d.ab_len;
+  A.ws_stride = (size_t)o * 32;
+  h->l_blocks = h->sm_count * bps;
+  if (h->l_ws.ensure(sizeof(double) * A.ws_stride * h->l_blocks)) return fail(-1002, "out of device memory for the lane workspace (%zu MB)", (sizeof(double) * A.ws_stride * h->l_blocks) >> 20);
+  A.ws = h->l_ws.as<double>();
+  h->l_ready = 1;
+  return 0;
+}
+
 static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
   if (d.autoreduce) return 0;                // auto-reduce runs on the table-driven kernel
   if (h->opt_kernel == 0) return 0;          // "kernel"=0 forces the table-driven, reference-order kernel
   if (h->T->nnz <= 0) return 0;
+  if (h->opt_kernel == 3) return host_lsched(h->mech_id) ? 3 : 0;     // lane kernel: every method
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return 0;
   if (d.o.Tstart == d.o.Tend) return 0;
   // "kernel"=2: the warp-group kernel -- on explicit request only: its results vary from run to run at the 1e-9
@@ -544,7 +607,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   const bool smem = kern == 1;
   int blocks = (nwork + h->threads - 1) / h->threads;
   if (blocks > h->max_blocks) blocks = h->max_blocks;
-  int rc = kern == 2 ? prepare_warp(h) : (smem ? prepare_smem(h) : ensure_workspace(h, blocks));
+  int rc = kern == 3 ? prepare_lane(h) : kern == 2 ? prepare_warp(h) : (smem ? prepare_smem(h) : ensure_workspace(h, blocks));
   if (rc) return rc;
   RosArgs a;
   a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
@@ -562,6 +625,12 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
   if (h->T->nnz == 0) {   // carbon: forward Euler
     CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
+  } else if (kern == 3) { // one cell per lane, one warp per block, persistent
+    int nb = (nwork + 31) / 32;
+    if (nb > h->l_blocks) nb = h->l_blocks;
+    if (h->sm_blocks_cap > 0 && nb > h->sm_blocks_cap) nb = h->sm_blocks_cap;
+    CUDA_TRY(launch_ros_lane(h->largs, a, nb, h->stream));
+    h->last_kernel = 3;
   } else if (kern == 2) { // one persistent block per SM, one cell per warp
     const int cpb = warp_cells_per_block(h->mech_id);
     int nb = (nwork + cpb - 1) / cpb;
@@ -593,7 +662,10 @@ struct DevIO {
 
 static void print_profile(gckpp_gpu_handle *h, const unsigned long long *sums)
 {
-  if (h->last_kernel == 2) {
+  if (h->last_kernel == 3) {
+    fprintf(stderr, "[gckpp profile] lane kernel, block 0, cycles: refill %llu load_y %llu fun(x3) %llu jac_rates %llu jac_sums %llu lu %llu stage_vectors %llu solves(x4) %llu error+accept %llu\n",
+            sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16]);
+  } else if (h->last_kernel == 2) {
     fprintf(stderr, "[gckpp profile] lead warp of group 0, block 0, cycles: load %llu fun0(vdot) %llu jac %llu lu_head %llu lu_tail %llu tail_solve %llu stage_rhs+vdot %llu solve_streams %llu accept %llu retire %llu rates %llu\n",
             sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18]);
     const char *kn[4] = {"vdot", "jvs", "lu", "solve"};

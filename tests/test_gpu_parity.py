@@ -77,10 +77,10 @@ def test_update_rconst_vs_oracle(solver, oracle):
     assert np.median(err[ro != 0]) < 1e-15
 
 
-KERNELS = {"warp": 2, "smem": 1, "table": 0}
+KERNELS = {"lane": 3, "warp": 2, "smem": 1, "table": 0}
 
 
-@pytest.mark.parametrize("kernel", ["warp", "smem", "table"])
+@pytest.mark.parametrize("kernel", ["lane", "warp", "smem", "table"])
 def test_integrate_fixture_replicated(solver, fx, kernel):
     """config 1: the Beijing cell, replicated; the 3-D model's own answer is 12 steps, Hexit 497.8023"""
     solver.set_option("kernel", KERNELS[kernel])
@@ -101,7 +101,7 @@ def _parity(c, co, floor=1e3):
     return rel
 
 
-@pytest.mark.parametrize("kernel", ["warp", "smem", "table"])
+@pytest.mark.parametrize("kernel", ["lane", "warp", "smem", "table"])
 @pytest.mark.parametrize("hstart", ["warm", "cold"])
 def test_integrate_grid_sample_vs_oracle(solver, oracle, hstart, kernel):
     solver.set_option("kernel", KERNELS[kernel])
@@ -166,7 +166,7 @@ def test_hg_mechanism_vs_oracle(lib, oracle):
     icntrl = np.zeros(20, np.int32); icntrl[[0, 2, 6, 14]] = [1, 4, 1, -1]
     rcntrl = np.zeros(20)
     co, isto, rsto, ierro = oracle.integrate("Hg", 0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
-    for kernel in ("warp", "smem", "table"):
+    for kernel in ("lane", "warp", "smem", "table"):
         s.set_option("kernel", KERNELS[kernel])
         c, ist, rst, ierr, _ = s.Integrate(0.0, 3600.0, conc, rconst, atol, rtol, icntrl, rcntrl)
         assert np.array_equal(ierr, ierro)
@@ -241,10 +241,12 @@ def test_autoreduce_vs_oracle(solver, oracle, fx, mode):
         assert np.allclose(rst[3], rsto[3], rtol=1e-12) and (rst[3] > 0).all()
 
 
+@pytest.mark.parametrize("kernel", ["default", "lane"])
 @pytest.mark.parametrize("method", [1, 2, 3, 5, 6])
-def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method):
+def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method, kernel):
     """ICNTRL(3) = 1 Ros2, 2 Ros3, 3 Ros4, 5 Rodas4, 6 Rang3 (gckpp_Integrator.F90:2062-2476): the table-driven
-    kernel takes over (the shared-memory kernel is Rodas3 only) and must follow the oracle step for step."""
+    kernel takes over by default (the shared-memory kernel is Rodas3 only) and must follow the oracle step for step;
+    the lane kernel runs every method too (FMA + re-associated sums: a few cells may take a different step count)"""
     g = grid.make_grid("4x5", limit=30000)
     rng = np.random.default_rng(method)
     idx = np.sort(rng.choice(30000, 200, replace=False))
@@ -253,14 +255,14 @@ def test_other_rosenbrock_methods_vs_oracle(solver, oracle, method):
                               np.ascontiguousarray(g["photol"][:, idx]), np.ascontiguousarray(g["khet"][:, idx]))
     icntrl = g["icntrl"].copy()
     icntrl[2] = method
-    solver.set_option("kernel", -1)      # the default choice; the library itself must fall back
+    solver.set_option("kernel", -1 if kernel == "default" else KERNELS[kernel])   # default: the library itself must fall back
     co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
     c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
     assert np.array_equal(ierr, ierro)
     rel = _parity(c, co)
     same = np.all(ist == isto, axis=0)
-    print("method %d: mean Nstp %.1f, cells with different steps %d, max rel err %.3e" % (method, ist[2].mean(), int((~same).sum()), rel.max()))
-    assert rel.max() <= 1e-4 and same.all()
+    print("method %d %s: mean Nstp %.1f, cells with different steps %d, max rel err %.3e" % (method, kernel, ist[2].mean(), int((~same).sum()), rel.max()))
+    assert rel.max() <= 1e-4 and (same.all() if kernel == "default" else (~same).sum() <= 2)
 
 
 def test_pipelined_host_entry_matches_serial(solver):
