@@ -773,6 +773,7 @@ static int finish_stats(gckpp_gpu_handle *h)
   if (getenv("GCKPP_PROFILE")) print_profile(h, sums);
   h->stats[3] = (double)sums[3]; h->stats[7] = (double)sums[0]; h->stats[8] = (double)sums[1];
   h->stats[10] = (double)sums[2];           // integrations that ended with IERR < 0 (first pass and retry)
+  h->stats[13] = h->last_kernel;
   if (h->stats[12] > 0) {                   // Update_RCONST: the last launch's time, scaled to the launches of the call
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->stats[1] = ms * h->stats[12];

@@ -987,12 +987,10 @@ template <class M>
 static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s)
 {
   auto k = ros_smem_kernel<M>;
-  static int configured = 0;
-  if (configured < P.s_total) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.s_total);
-    if (e != cudaSuccess) return e;
-    configured = P.s_total;
-  }
+  // the opt-in is a per-DEVICE attribute of the function (one process may hold handles on several GPUs): set it on
+  // every launch -- it is cheap -- rather than cache it per process
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.s_total);
+  if (e != cudaSuccess) return e;
   k<<<blocks, NT, P.s_total, s>>>(P, a);
   return cudaGetLastError();
 }

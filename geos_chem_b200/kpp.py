@@ -322,7 +322,7 @@ class KppSolver:
         s = (C.c_double * 16)()
         self.L.gckpp_gpu_last_stats(self.h, s)
         keys = ("integrate_ms", "rconst_ms", "copy_ms", "cells", "retried", "failed_twice", "launches", "sum_nstp",
-                "sum_nacc", "device_ms", "failed_integrations", "waves")
+                "sum_nacc", "device_ms", "failed_integrations", "waves", "rconst_launches", "kernel")
         return dict(zip(keys, (float(x) for x in s)))
 
 

@@ -340,3 +340,88 @@ def test_carbon_forward_euler_vs_oracle(lib, oracle, icntrl16):
     assert np.array_equal(c, co)
     if icntrl16 == 1:
         assert (c[:d["nvar"]] >= 0).all()
+
+
+def test_retry_pass_with_forced_failures(solver, oracle):
+    """Do_FullChem's second try (GeosCore/fullchem_mod.F90:1138-1162): a cell whose integration fails is restored and
+    integrated again with RCNTRL(3) = 0 (default first step).  Failures are forced here: ICNTRL(4) = 32 steps at most,
+    and a tenth of the cells start from Hstart = 1e-20 s, which needs ~30 steps just to grow the step (IERR -6).  The GPU
+    result of the two passes must equal the oracle run the same way, cell for cell (status codes, concentrations
+    within the 1e-4 bar), and the call must report how many cells were retried / failed twice."""
+    n = 800
+    g = grid.make_grid("4x5", limit=n)
+    rng = np.random.default_rng(3)
+    hs = g["hstart"].copy()
+    slow = rng.uniform(size=n) < 0.1
+    hs[slow] = 1e-20
+    icntrl = g["icntrl"].copy(); icntrl[3] = 32
+    rc = oracle.update_rconst("fullchem", g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"])
+    co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, g["conc"], rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
+    bad = np.flatnonzero(ierro < 0)
+    assert bad.size >= 20 and (ierro[bad] == -6).all()
+    c2, ist2, rst2, ierr2 = oracle.integrate("fullchem", 0.0, 1200.0, np.ascontiguousarray(g["conc"][:, bad]),
+                                             np.ascontiguousarray(rc[:, bad]), g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=None)
+    co[:, bad], isto[:, bad], ierro[bad] = c2, ist2, ierr2
+    for kernel in (1, 0):
+        solver.set_option("kernel", kernel)
+        solver.set_option("retry", 1)
+        try:
+            c, ist, rst, ierr, nf = solver.Integrate(0.0, 1200.0, g["conc"], rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
+            st = solver.last_stats()
+        finally:
+            solver.set_option("retry", 0)
+        assert np.array_equal(ierr, ierro)
+        ok = ierr == 1
+        assert _parity(c[:, ok], co[:, ok]).max() <= 1e-4
+        assert np.array_equal(ist[2, ok], isto[2, ok]) or (ist[2, ok] != isto[2, ok]).sum() <= 1
+        assert st["retried"] == bad.size and st["failed_twice"] == (ierr2 < 0).sum() == nf
+        print("kernel %d: %d cells retried, %d failed twice" % (kernel, bad.size, int((ierr2 < 0).sum())))
+        # without the retry the same call reports the first-pass failures
+        c1, _, _, ierr1, _ = solver.Integrate(0.0, 1200.0, g["conc"], rc, g["atol"], g["rtol"], icntrl, g["rcntrl"], hstart=hs)
+        assert (ierr1[bad] == -6).all() and (ierr1 < 0).sum() == bad.size
+
+
+@pytest.mark.parametrize("case", ["icntrl4", "method", "hmin", "facmin", "tol"])
+def test_option_errors_match_the_reference(solver, oracle, case):
+    """Rosenbrock()'s input checks (gckpp_Integrator.F90:345-467): IERR -1 (ICNTRL(4) < 0), -2 (unknown method), -5
+    (tolerances <= 0): every cell reports the code, nothing is integrated, and the oracle agrees.  -3 (Hmin/Hmax/Hstart
+    < 0) and -4 (FacMin..FacSafe <= 0) cannot be reached through Integrate: its merge keeps only POSITIVE user RCNTRL
+    values (gckpp_Integrator.F90:116), so a negative Hmin or FacMin is silently replaced by the default and the
+    integration runs -- here as there."""
+    g = grid.make_grid("4x5", limit=64)
+    icntrl, rcntrl, atol, rtol = g["icntrl"].copy(), g["rcntrl"].copy(), g["atol"].copy(), g["rtol"].copy()
+    want = {"icntrl4": -1, "method": -2, "hmin": 1, "facmin": 1, "tol": -5}[case]
+    if case == "icntrl4":
+        icntrl[3] = -1
+    elif case == "method":
+        icntrl[2] = 9
+    elif case == "hmin":
+        rcntrl[0] = -1.0
+    elif case == "facmin":
+        rcntrl[3] = -0.5
+    else:
+        atol[5] = 0.0
+    rc = oracle.update_rconst("fullchem", g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"])
+    _, _, _, ierro = oracle.integrate("fullchem", 0.0, 1200.0, g["conc"], rc, atol, rtol, icntrl, rcntrl, hstart=g["hstart"])
+    assert (ierro == want).all()
+    c, ist, rst, ierr, code = solver.Integrate(0.0, 1200.0, g["conc"], rc, atol, rtol, icntrl, rcntrl, hstart=g["hstart"])
+    assert code == want and (ierr == want).all()
+
+
+def test_handles_on_two_devices_from_one_process(lib, fx):
+    """INTEGRATION.md's threading model: one host process drives several GPUs through independent handles.  The
+    shared-memory opt-in of the kernels is a per-device function attribute, so the second device must launch too."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = grid.replicate_fixture(97, fx)
+    outs = []
+    for devi in (0, 1):
+        s = kpp.KppSolver("fullchem", device=devi, max_cells=4096)
+        for kernel in (1, 3):
+            s.set_option("kernel", kernel)
+            c, ist, rst, ierr, _ = s.Integrate(0.0, r["dt"], r["conc"], r["rconst"], r["atol"], r["rtol"], r["icntrl"], r["rcntrl"])
+            assert (ierr == 1).all() and (ist[kpp.Nstp] == fx["fileTotSteps"]).all()
+            outs.append(c)
+        s.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
