@@ -89,7 +89,7 @@ CONFIGS = {
     # BASELINE.json configs: name -> (mechanism, grid, description)
     "1": ("fullchem", "4x5", "KPP/standalone Beijing sample cell replicated over a 4x5x72 grid (zero divergence)"),
     "2": ("fullchem", "4x5", "4x5 global, 72 levels"),
-    "3": ("fullchem", "2x25", "2x2.5 global, 72 levels, sharded by (I,J) columns over the GPUs"),
+    "3": ("fullchem", "2x2.5", "2x2.5 global, 72 levels, sharded by (I,J) columns over the GPUs"),
     "4": ("fullchem", "c180", "C180 cubed-sphere equivalent, 72 levels, sharded by columns, processed in waves"),
     "5-hg": ("Hg", "4x5", "Hg mechanism (small-mechanism path) on the 4x5x72 cells"),
     "5-carbon": ("carbon", "4x5", "carbon mechanism (forward Euler) on the 4x5x72 cells"),
@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json config (default: 2 on one GPU, 3 on several)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="N>1: strong (default) shards the config's grid, weak gives every GPU a grid-sized share")
-    ap.add_argument("--grid", default=None, help="override the config's grid (4x5, 2x25, c180)")
+    ap.add_argument("--grid", default=None, help="override the config's grid (4x5, 2x2.5, c180)")
     ap.add_argument("--hstart", default="warm", choices=["warm", "cold"])
     ap.add_argument("--cells", type=int, default=0, help="debug: subsample the per-GPU cells to this many")
     ap.add_argument("--shard-of", type=int, default=0, help="debug: take shard --shard-rank of this many (e.g. one eighth of C180 on one GPU)")
