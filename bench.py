@@ -105,9 +105,9 @@ def resolve(args, world):
     """fill in config / scaling defaults: N=1 -> config 2 (the configuration the metric is quoted on);
     N>1 -> config 3 strong-scaled (943,488 cells sharded by column), --scaling weak keeps a 4x5-sized share per GPU"""
     if args.config is None:
-        args.config = "2" if (world == 1 or args.scaling == "weak") else "3"
+        args.config = "2" if ((world == 1 and not args.shard_of) or args.scaling == "weak") else "3"
     if args.scaling is None:
-        args.scaling = "strong" if world > 1 else "weak"
+        args.scaling = "strong" if (world > 1 or args.shard_of) else "weak"
     args.mech, cfg_grid, args.desc = CONFIGS[args.config]
     if args.grid is None:
         args.grid = cfg_grid

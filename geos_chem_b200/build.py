@@ -29,6 +29,8 @@ UNITS = {
     "ros_smem.cu": (["-DSMEM_PROFILE"] if os.environ.get("GCKPP_SMEM_PROFILE") else []) + os.environ.get("GCKPP_SMEM_DEFS", "").split(),
     # production kernel: one warp per cell
     "ros_warp.cu": (["-DWARP_PROFILE"] if os.environ.get("GCKPP_WARP_PROFILE") else []) + os.environ.get("GCKPP_WARP_DEFS", "").split(),
+    # Do_FullChem's pieces around the integration, reference operation order
+    "post.cu": ["-fmad=false"],
     # one cell per lane, streamed workspace
     "ros_lane.cu": (["-DLANE_PROFILE"] if os.environ.get("GCKPP_LANE_PROFILE") else []) + os.environ.get("GCKPP_LANE_DEFS", "").split(),
     "gckpp_gpu.cu": os.environ.get("GCKPP_SMEM_DEFS", "").split() + os.environ.get("GCKPP_WARP_DEFS", "").split(),

@@ -136,6 +136,8 @@ struct gckpp_gpu_handle {
   int l_ready = 0, l_blocks = 0;
   LaneArgs largs{};
   DevBuf l_tab[7], l_lit, l_ws;
+  const double *ohr_coef = nullptr; const int *ohr_rxn = nullptr, *ohr_spc = nullptr;   // Get_OHreactivity terms (device)
+  DevBuf small;                            // the little index lists of the post-integrate entry points
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -232,6 +234,10 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
     UP(j_ptr, T->j_ptr, T->nnz + 1, int); UP(j_coef, T->j_coef, T->nj, double); UP(j_b, T->j_b, T->nj, int);
   }
   UP(lit, T->lit, T->nlit, double);
+  if (T->nohr > 0) {
+    if ((rc = upload<double>(h, T->ohr_coef, (size_t)T->nohr, &h->ohr_coef)) || (rc = upload<int>(h, T->ohr_rxn, (size_t)T->nohr, &h->ohr_rxn)) ||
+        (rc = upload<int>(h, T->ohr_spc, (size_t)T->nohr, &h->ohr_spc))) { gckpp_gpu_finalize(h); return rc; }
+  }
 #undef UP
   h->L = make_layout(T);
   h->max_blocks = h->sm_count * h->blocks_per_sm;
@@ -254,6 +260,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
                     &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
                     &h->l_tab[0], &h->l_tab[1], &h->l_tab[2], &h->l_tab[3], &h->l_tab[4], &h->l_tab[5], &h->l_tab[6], &h->l_lit, &h->l_ws,
+                    &h->small,
                     &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   free_slots(h);
@@ -589,6 +596,9 @@ static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
   if (h->opt_kernel == 0) return 0;          // "kernel"=0 forces the table-driven, reference-order kernel
   if (h->T->nnz <= 0) return 0;
   if (h->opt_kernel == 3) return host_lsched(h->mech_id) ? 3 : 0;     // lane kernel: every method
+  // small mechanisms (Hg: 32 species, 161 matrix entries): the lane kernel is the default -- a warp's whole
+  // workspace is 150 KB, seven warps fit an SM, 2.7 M cells/s against 1.1 M for the block kernel (profiles/r02r_hg_bench.log)
+  if (h->opt_kernel < 0 && h->T->nvar <= 64 && host_lsched(h->mech_id)) return 3;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return 0;
   if (d.o.Tstart == d.o.Tend) return 0;
   // "kernel"=2: the warp-group kernel -- on explicit request only: its results vary from run to run at the 1e-9
@@ -1053,6 +1063,142 @@ extern "C" int gckpp_gpu_fun(gckpp_gpu_handle_t *h, int ncell, const double *con
   if (vdot) CUDA_TRY(cudaMemcpyAsync(vdot, h->s_conc_out.p, sizeof(double) * T->nvar * nc, cudaMemcpyDeviceToHost, h->stream));
   if (aout) CUDA_TRY(cudaMemcpyAsync(aout, h->scratch.p, sizeof(double) * T->nreact * nc, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- the pieces of Do_FullChem around the integration (post.cu) -------------------------------------------------
+// the small host lists of a call, packed into one device buffer: [ints][doubles][bytes]
+static int stage_small(gckpp_gpu_handle *h, const int32_t *ints, int ni, const double *dbl, int nd, const uint8_t *bytes, int nb,
+                       const int **d_int, const double **d_dbl, const unsigned char **d_bytes)
+{
+  const size_t oi = 0, od = ((size_t)ni * 4 + 7) & ~(size_t)7, ob = od + (size_t)nd * 8, tot = ob + (size_t)nb + 16;
+  if (h->small.ensure(tot)) return fail(-1002, "out of device memory");
+  char *base = (char *)h->small.p;
+  if (ni) CUDA_TRY(cudaMemcpyAsync(base + oi, ints, (size_t)ni * 4, cudaMemcpyHostToDevice, h->stream));
+  if (nd) CUDA_TRY(cudaMemcpyAsync(base + od, dbl, (size_t)nd * 8, cudaMemcpyHostToDevice, h->stream));
+  if (nb) CUDA_TRY(cudaMemcpyAsync(base + ob, bytes, (size_t)nb, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));       // the host lists may be temporaries of the caller
+  *d_int = (const int *)(base + oi); *d_dbl = (const double *)(base + od); *d_bytes = nb ? (const unsigned char *)(base + ob) : nullptr;
+  return 0;
+}
+static int check_ids(const gckpp_host_tables_t *T, const int32_t *ids, int n, const char *what)
+{
+  if (n < 0 || (n > 0 && !ids)) return fail(-10, "%s: bad index list", what);
+  for (int k = 0; k < n; k++) if (ids[k] < 0 || ids[k] >= T->nspec) return fail(-10, "%s: species index %d out of range", what, ids[k]);
+  return 0;
+}
+
+extern "C" int gckpp_gpu_zero_species_device(gckpp_gpu_handle_t *h, int ncell, double *conc, int n, const int32_t *ids0)
+{
+  if (!h || !conc || ncell < 0) return fail(-10, "gckpp_gpu_zero_species: bad arguments");
+  int rc;
+  if ((rc = check_ids(h->T, ids0, n, "gckpp_gpu_zero_species"))) return rc;
+  if (ncell == 0 || n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int *di; const double *dd; const unsigned char *db;
+  if ((rc = stage_small(h, ids0, n, nullptr, 0, nullptr, 0, &di, &dd, &db))) return rc;
+  CUDA_TRY(launch_zero_species(conc, ncell, di, n, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_post_integrate_device(gckpp_gpu_handle_t *h, int ncell, double *conc, int nscale, const int32_t *scale_ids0,
+                                               const double *scale_div, const uint8_t *spc_mask, float *negatives)
+{
+  if (!h || !conc || ncell < 0 || (nscale > 0 && !scale_div)) return fail(-10, "gckpp_gpu_post_integrate: bad arguments");
+  int rc;
+  if ((rc = check_ids(h->T, scale_ids0, nscale, "gckpp_gpu_post_integrate"))) return rc;
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int *di; const double *dd; const unsigned char *db;
+  if ((rc = stage_small(h, scale_ids0, nscale, scale_div, nscale, spc_mask, spc_mask ? h->T->nspec : 0, &di, &dd, &db))) return rc;
+  CUDA_TRY(launch_post_integrate(conc, ncell, h->T->nspec, di, dd, nscale, db, negatives, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_prod_loss_device(gckpp_gpu_handle_t *h, int ncell, const double *conc, double dt, int nslots,
+                                          const int32_t *ids0, double *out)
+{
+  if (!h || !conc || !out || ncell < 0 || !(dt > 0.0)) return fail(-10, "gckpp_gpu_prod_loss: bad arguments");
+  int rc;
+  if ((rc = check_ids(h->T, ids0, nslots, "gckpp_gpu_prod_loss"))) return rc;
+  if (ncell == 0 || nslots == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int *di; const double *dd; const unsigned char *db;
+  if ((rc = stage_small(h, ids0, nslots, nullptr, 0, nullptr, 0, &di, &dd, &db))) return rc;
+  CUDA_TRY(launch_prod_loss(conc, ncell, dt, di, nslots, out, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_oh_reactivity_device(gckpp_gpu_handle_t *h, int ncell, const double *conc, const double *rconst, double *ohreact)
+{
+  if (!h || !conc || !rconst || !ohreact || ncell < 0) return fail(-10, "gckpp_gpu_oh_reactivity: bad arguments");
+  if (h->T->nohr <= 0) return fail(-11, "the mechanism has no Get_OHreactivity");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(launch_oh_reactivity(conc, rconst, ncell, h->ohr_coef, h->ohr_rxn, h->ohr_spc, h->T->nohr, ohreact, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// host-array variants: stage conc (and rconst) through the handle's buffers
+extern "C" int gckpp_gpu_zero_species(gckpp_gpu_handle_t *h, int ncell, double *conc, int n, const int32_t *ids0)
+{
+  if (!h || !conc || ncell < 0) return fail(-10, "gckpp_gpu_zero_species: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(double) * h->T->nspec * (size_t)ncell;
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, bytes))) return rc;
+  if ((rc = gckpp_gpu_zero_species_device(h, ncell, h->s_conc_in.as<double>(), n, ids0))) return rc;
+  CUDA_TRY(cudaMemcpy(conc, h->s_conc_in.p, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_post_integrate(gckpp_gpu_handle_t *h, int ncell, double *conc, int nscale, const int32_t *scale_ids0,
+                                        const double *scale_div, const uint8_t *spc_mask, float *negatives)
+{
+  if (!h || !conc || ncell < 0) return fail(-10, "gckpp_gpu_post_integrate: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(double) * h->T->nspec * (size_t)ncell;
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, bytes))) return rc;
+  if (negatives && (rc = h2d(h, h->s_hstart, negatives, sizeof(float) * (size_t)ncell))) return rc;
+  if ((rc = gckpp_gpu_post_integrate_device(h, ncell, h->s_conc_in.as<double>(), nscale, scale_ids0, scale_div, spc_mask,
+                                            negatives ? h->s_hstart.as<float>() : nullptr))) return rc;
+  CUDA_TRY(cudaMemcpy(conc, h->s_conc_in.p, bytes, cudaMemcpyDeviceToHost));
+  if (negatives) CUDA_TRY(cudaMemcpy(negatives, h->s_hstart.p, sizeof(float) * (size_t)ncell, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_prod_loss(gckpp_gpu_handle_t *h, int ncell, const double *conc, double dt, int nslots,
+                                   const int32_t *ids0, double *out)
+{
+  if (!h || !conc || !out || ncell < 0 || nslots < 0) return fail(-10, "gckpp_gpu_prod_loss: bad arguments");
+  if (ncell == 0 || nslots == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, sizeof(double) * h->T->nspec * (size_t)ncell))) return rc;
+  if (h->s_conc_out.ensure(sizeof(double) * (size_t)nslots * ncell)) return fail(-1002, "out of device memory");
+  if ((rc = gckpp_gpu_prod_loss_device(h, ncell, h->s_conc_in.as<double>(), dt, nslots, ids0, h->s_conc_out.as<double>()))) return rc;
+  CUDA_TRY(cudaMemcpy(out, h->s_conc_out.p, sizeof(double) * (size_t)nslots * ncell, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int gckpp_gpu_oh_reactivity(gckpp_gpu_handle_t *h, int ncell, const double *conc, const double *rconst, double *ohreact)
+{
+  if (!h || !conc || !rconst || !ohreact || ncell < 0) return fail(-10, "gckpp_gpu_oh_reactivity: bad arguments");
+  if (ncell == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = h2d(h, h->s_conc_in, conc, sizeof(double) * h->T->nspec * (size_t)ncell))) return rc;
+  if ((rc = h2d(h, h->s_rconst, rconst, sizeof(double) * h->T->nreact * (size_t)ncell))) return rc;
+  if (h->s_rst.ensure(sizeof(double) * (size_t)ncell)) return fail(-1002, "out of device memory");
+  if ((rc = gckpp_gpu_oh_reactivity_device(h, ncell, h->s_conc_in.as<double>(), h->s_rconst.as<double>(), h->s_rst.as<double>()))) return rc;
+  CUDA_TRY(cudaMemcpy(ohreact, h->s_rst.p, sizeof(double) * (size_t)ncell, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -25,3 +25,11 @@ cudaError_t launch_select_active(int ncell, int c0, int c1, const uint8_t *activ
                                  int *cell_list, int *count, cudaStream_t s);
 cudaError_t launch_select_failed(int c0, int c1, const int *ierr, int *cell_list, int *count, cudaStream_t s);
 cudaError_t measure_fp64_peak(double *tflops, double *ms);
+
+// post.cu (compiled with -fmad=false): the pieces of Do_FullChem around the integration
+cudaError_t launch_zero_species(double *conc, int ncell, const int *ids, int n, cudaStream_t s);
+cudaError_t launch_post_integrate(double *conc, int ncell, int nspec, const int *scale_ids, const double *scale_div, int nscale,
+                                  const unsigned char *mask, float *negatives, cudaStream_t s);
+cudaError_t launch_prod_loss(const double *conc, int ncell, double dt, const int *ids, int nslots, double *out, cudaStream_t s);
+cudaError_t launch_oh_reactivity(const double *conc, const double *rconst, int ncell, const double *coef, const int *rxn,
+                                 const int *spc, int nterms, double *out, cudaStream_t s);

@@ -14,6 +14,7 @@ struct gckpp_host_tables_t {
   const int *b_term;                                   // [nb][4]   Jac_SP partials
   const int *j_ptr; const double *j_coef; const int *j_b; int nj;     // JVS sums
   const double *lit; int nlit;
+  const double *ohr_coef; const int *ohr_rxn, *ohr_spc; int nohr;   // Get_OHreactivity: sum coef * RCONST(rxn) [* C(spc)]
 };
 
 // Round/bundle schedules of the shared-memory kernel (kppgen/sched.py documents the encoding).

@@ -67,6 +67,11 @@ def load_library(path=None):
     L.gckpp_gpu_plan_info.argtypes = [C.c_int, ip]
     L.gckpp_gpu_set_keep_active.argtypes = [vp, C.c_int, ip]
     L.gckpp_gpu_warp_plan.argtypes = [C.c_int, ip, C.c_int, vp, C.c_int64]
+    for sfx in ("", "_device"):
+        getattr(L, "gckpp_gpu_zero_species" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        getattr(L, "gckpp_gpu_post_integrate" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
+        getattr(L, "gckpp_gpu_prod_loss" + sfx).argtypes = [vp, C.c_int, vp, C.c_double, C.c_int, vp, vp]
+        getattr(L, "gckpp_gpu_oh_reactivity" + sfx).argtypes = [vp, C.c_int, vp, vp, vp]
     _lib = L
     return L
 
@@ -75,7 +80,10 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_integrate", "gckpp_gpu_integrate_device", "gckpp_gpu_update_rconst",
            "gckpp_gpu_update_rconst_device", "gckpp_gpu_fun", "gckpp_gpu_jac", "gckpp_gpu_decomp",
            "gckpp_gpu_solve", "gckpp_gpu_last_stats", "gckpp_gpu_last_error", "gckpp_gpu_set_stream",
-           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active", "gckpp_gpu_warp_plan"]
+           "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active", "gckpp_gpu_warp_plan",
+           "gckpp_gpu_zero_species", "gckpp_gpu_zero_species_device", "gckpp_gpu_post_integrate",
+           "gckpp_gpu_post_integrate_device", "gckpp_gpu_prod_loss", "gckpp_gpu_prod_loss_device",
+           "gckpp_gpu_oh_reactivity", "gckpp_gpu_oh_reactivity_device"]
 
 
 def plan_info(mech):
@@ -317,6 +325,76 @@ class KppSolver:
         x = _np(X, np.float64).copy()
         self._check(self.L.gckpp_gpu_solve(self.h, j.shape[1], _ptr(j), _ptr(x)), "KppSolve")
         return x
+
+    # ------------------------------------------------------------------ Do_FullChem's pieces around the integration
+    # numpy arrays are staged through the host entry points (a new array is returned), torch CUDA tensors are
+    # modified in place on the device
+    def _ids(self, ids0):
+        a = np.ascontiguousarray(ids0, np.int32).reshape(-1)
+        return a, (a.ctypes.data_as(C.c_void_p) if a.size else None)
+
+    def zero_species(self, C_io, ids0):
+        """C(PL_Kpp_Id(F)) = 0 for the prod/loss family species (GeosCore/fullchem_mod.F90:941-946)"""
+        ids, pi = self._ids(ids0)
+        if _is_torch(C_io):
+            self._torch_stream(C_io)
+            self._check(self.L.gckpp_gpu_zero_species_device(self.h, C_io.shape[1], _ptr(C_io), ids.size, pi), "zero_species")
+            return C_io
+        c = _np(C_io, np.float64).copy()
+        self._check(self.L.gckpp_gpu_zero_species(self.h, c.shape[1], _ptr(c), ids.size, pi), "zero_species")
+        return c
+
+    def post_integrate(self, C_io, scale_ids0=(), scale_div=(), spc_mask=None, negatives=None):
+        """fullchem_ConvertEquivToAlk (C(id) = C(id) / div), the KppNegatives count and C = MAX(C, 0) over the species
+        with spc_mask != 0 (GeosCore/fullchem_mod.F90:1284-1287, 1326-1348).  Returns (C, negatives)."""
+        ids, pi = self._ids(scale_ids0)
+        div = np.ascontiguousarray(scale_div, np.float64).reshape(-1)
+        if div.size != ids.size:
+            raise ValueError("scale_ids0 and scale_div differ in length")
+        mask = None if spc_mask is None else np.ascontiguousarray(spc_mask, np.uint8)
+        if mask is not None and mask.shape != (self.dims["nspec"],):
+            raise ValueError("spc_mask: expected [%d]" % self.dims["nspec"])
+        pd = div.ctypes.data_as(C.c_void_p) if div.size else None
+        pm = mask.ctypes.data_as(C.c_void_p) if mask is not None else None
+        if _is_torch(C_io):
+            self._torch_stream(C_io, negatives)
+            self._check(self.L.gckpp_gpu_post_integrate_device(self.h, C_io.shape[1], _ptr(C_io), ids.size, pi, pd, pm,
+                                                               _ptr(negatives)), "post_integrate")
+            return C_io, negatives
+        c = _np(C_io, np.float64).copy()
+        neg = None if negatives is None else np.ascontiguousarray(negatives, np.float32).copy()
+        self._check(self.L.gckpp_gpu_post_integrate(self.h, c.shape[1], _ptr(c), ids.size, pi, pd, pm, _ptr(neg)), "post_integrate")
+        return c, neg
+
+    def prod_loss(self, C_in, dt, ids0, out=None):
+        """State_Diag%Prod / %Loss(slot) = C(KppId(slot)) / DT (GeosCore/fullchem_mod.F90:1463-1492) -> [nslots, ncell]"""
+        ids, pi = self._ids(ids0)
+        if _is_torch(C_in):
+            import torch
+            if out is None:
+                out = torch.empty((ids.size, C_in.shape[1]), dtype=torch.float64, device=C_in.device)
+            self._torch_stream(C_in, out)
+            self._check(self.L.gckpp_gpu_prod_loss_device(self.h, C_in.shape[1], _ptr(C_in), float(dt), ids.size, pi, _ptr(out)), "prod_loss")
+            return out
+        c = _np(C_in, np.float64)
+        out = np.empty((ids.size, c.shape[1]), np.float64)
+        self._check(self.L.gckpp_gpu_prod_loss(self.h, c.shape[1], _ptr(c), float(dt), ids.size, pi, _ptr(out)), "prod_loss")
+        return out
+
+    def Get_OHreactivity(self, C_in, RCONST, out=None):
+        """Get_OHreactivity(CC, RR, OHreact) of KPP/fullchem/gckpp_Util.F90:983-1040 over cells -> [ncell] (1/s)"""
+        if _is_torch(C_in):
+            import torch
+            if out is None:
+                out = torch.empty((C_in.shape[1],), dtype=torch.float64, device=C_in.device)
+            self._torch_stream(C_in, RCONST, out)
+            self._check(self.L.gckpp_gpu_oh_reactivity_device(self.h, C_in.shape[1], _ptr(C_in), _ptr(RCONST), _ptr(out)), "Get_OHreactivity")
+            return out
+        c = _np(C_in, np.float64)
+        rc = _np(RCONST, np.float64, (self.dims["nreact"], c.shape[1]), "RCONST")
+        out = np.empty((c.shape[1],), np.float64)
+        self._check(self.L.gckpp_gpu_oh_reactivity(self.h, c.shape[1], _ptr(c), _ptr(rc), _ptr(out)), "Get_OHreactivity")
+        return out
 
     def last_stats(self):
         s = (C.c_double * 16)()

@@ -84,6 +84,7 @@ class Mechanism:
             self.B = [parse_expr(e) for e in d["B"]]
             self.JVS = [parse_expr(e) for e in d["JVS"]]
         self.rconst = d["rconst"]
+        self.ohreact = d.get("ohreact", [])   # Get_OHreactivity terms [coef, reaction, species or -1] (gckpp_Util.F90)
         # which ODE-function form the mechanism's FunTemplate calls:
         #   fullchem: Fun_SPLIT (KPP/fullchem/gckpp_Integrator.F90:2503)
         #   Hg, carbon: aggregate Fun (KPP/Hg/gckpp_Integrator.F90:1342-1370, KPP/carbon/gckpp_Integrator.F90)

@@ -123,6 +123,30 @@ int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *handle, int ncell,
 int gckpp_gpu_fun(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst,
                   double *vdot, double *aout);
 
+/* The pieces of Do_FullChem around the integration, so that the chemical state can stay on the device for a whole
+ * chemistry step (`_device`: conc / rconst / outputs are device pointers; the others stage host arrays).  The small
+ * index lists are always host pointers.  conc is [NSPEC][ncell], cell-fastest, modified in place.
+ *   zero_species    GeosCore/fullchem_mod.F90:941-946: C(PL_Kpp_Id(F)) = 0 for the n prod/loss family species ids0 (0-based)
+ *   post_integrate  :1284-1287 fullchem_ConvertEquivToAlk (KPP/fullchem/fullchem_SulfurChemFuncs.F90:94-105):
+ *                   C(scale_ids0[k]) = C / scale_div[k] (the host passes MW * 7.0e-5; nscale = 0 when sulfate_mod does it);
+ *                   :1326-1348 for every species with spc_mask[s] != 0 (Map_KppSpc > 0; NULL = all): negatives[cell] +=
+ *                   1 per negative concentration (State_Diag%KppNegatives, REAL*4, may be NULL), then C = MAX(C, 0)
+ *   prod_loss       :1463-1492: out[s][cell] = C(ids0[s]) / dt for the nslots prod or loss slots
+ *   oh_reactivity   KPP/fullchem/gckpp_Util.F90:983-1040 Get_OHreactivity(C, RCONST) -> ohreact[ncell] (fullchem, Hg) */
+int gckpp_gpu_zero_species(gckpp_gpu_handle_t *handle, int ncell, double *conc, int n, const int32_t *ids0);
+int gckpp_gpu_zero_species_device(gckpp_gpu_handle_t *handle, int ncell, double *conc, int n, const int32_t *ids0);
+int gckpp_gpu_post_integrate(gckpp_gpu_handle_t *handle, int ncell, double *conc, int nscale, const int32_t *scale_ids0,
+                             const double *scale_div, const uint8_t *spc_mask, float *negatives);
+int gckpp_gpu_post_integrate_device(gckpp_gpu_handle_t *handle, int ncell, double *conc, int nscale, const int32_t *scale_ids0,
+                                    const double *scale_div, const uint8_t *spc_mask, float *negatives);
+int gckpp_gpu_prod_loss(gckpp_gpu_handle_t *handle, int ncell, const double *conc, double dt, int nslots,
+                        const int32_t *ids0, double *out);
+int gckpp_gpu_prod_loss_device(gckpp_gpu_handle_t *handle, int ncell, const double *conc, double dt, int nslots,
+                               const int32_t *ids0, double *out);
+int gckpp_gpu_oh_reactivity(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst, double *ohreact);
+int gckpp_gpu_oh_reactivity_device(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst,
+                                   double *ohreact);
+
 /* Pieces exposed for parity tests (host pointers, cell-fastest):
  *   jac:    Jac_SP  -> jvs [LU_NONZERO][ncell]
  *   decomp: KppDecomp in place on jvs; ier[ncell] = 0 or the 1-based singular row

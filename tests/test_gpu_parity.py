@@ -425,3 +425,46 @@ def test_handles_on_two_devices_from_one_process(lib, fx):
             outs.append(c)
         s.close()
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
+def test_post_integrate_pieces_vs_oracle(solver, oracle):
+    """the lines of Do_FullChem around the integration (family zeroing, ConvertEquivToAlk, negatives count + clip,
+    prod/loss, Get_OHreactivity): GPU kernels against the numpy restatement, bit for bit, on host arrays and in place
+    on device tensors.  Parity unpinned by the reference (no vectors exist for these lines)."""
+    import torch
+    from oracle import post_oracle as po
+    from geos_chem_b200.kppgen import ir
+    m = ir.load("fullchem")
+    g = grid.make_grid("4x5", limit=3001)
+    rng = np.random.default_rng(23)
+    conc = g["conc"].copy()
+    conc[rng.integers(0, 356, 4000), rng.integers(0, 3001, 4000)] *= -1.0      # some negatives to clip
+    rc = oracle.update_rconst("fullchem", g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"])
+    fam = [m.ind[k] for k in ("POx", "LOx", "PCO", "LCO", "PSO4", "LCH4", "PH2O2")]
+    alk = [m.ind["SALAAL"], m.ind["SALCAL"]]
+    div = [31.4 * 7.0e-5, 31.4 * 7.0e-5]
+    mask = (rng.uniform(size=356) < 0.9).astype(np.uint8)
+    neg0 = rng.integers(0, 3, 3001).astype(np.float32)
+    # host arrays
+    assert np.array_equal(solver.zero_species(conc, fam), po.zero_species(conc, fam))
+    c, neg = solver.post_integrate(conc, alk, div, mask, neg0)
+    co, nego = po.post_integrate(conc, alk, div, mask, neg0)
+    assert np.array_equal(c, co) and np.array_equal(neg, nego) and (nego > neg0).any()
+    assert (c[mask != 0] >= 0).all() and (c[mask == 0] < 0).any()
+    assert np.array_equal(solver.prod_loss(conc, 1200.0, fam), po.prod_loss(conc, 1200.0, fam))
+    oh = solver.Get_OHreactivity(g["conc"], rc)
+    oho = po.oh_reactivity(m.ohreact, g["conc"], rc)
+    assert np.array_equal(oh, oho) and (oh > 0).all()
+    print("OH reactivity: median %.3e 1/s, %d terms" % (np.median(oh), len(m.ohreact)))
+    # device tensors, in place
+    dev = torch.device("cuda", 0)
+    tc = torch.from_numpy(conc).to(dev)
+    tn = torch.from_numpy(neg0).to(dev)
+    solver.zero_species(tc, fam)
+    solver.post_integrate(tc, alk, div, mask, tn)
+    c2, n2 = po.post_integrate(po.zero_species(conc, fam), alk, div, mask, neg0)
+    assert np.array_equal(tc.cpu().numpy(), c2) and np.array_equal(tn.cpu().numpy(), n2)
+    toh = solver.Get_OHreactivity(torch.from_numpy(g["conc"]).to(dev), torch.from_numpy(rc).to(dev))
+    assert np.array_equal(toh.cpu().numpy(), oho)
+    tpl = solver.prod_loss(tc, 1200.0, fam)
+    assert np.array_equal(tpl.cpu().numpy(), po.prod_loss(c2, 1200.0, fam))
