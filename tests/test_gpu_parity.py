@@ -339,7 +339,11 @@ def test_carbon_forward_euler_vs_oracle(lib, oracle, icntrl16):
     assert np.array_equal(ierr, ierro) and np.array_equal(ist, isto)
     assert np.array_equal(c, co)
     if icntrl16 == 1:
-        assert (c[:d["nvar"]] >= 0).all()
+        assert (c[:d["nvar"]] >= 0).all() and (ierr == 1).all()      # clipped; the final IERR = 1 overwrites the -9
+    if icntrl16 == 2:
+        # a negative entry makes ForwardEuler RETURN with IERR = -9 before "Y = Ynew": the cell keeps its input
+        bad = ierr == -9
+        assert bad.any() and (~bad).any() and np.array_equal(c[:, bad], conc[:, bad]) and (ierr[~bad] == 1).all()
 
 
 def test_retry_pass_with_forced_failures(solver, oracle):
