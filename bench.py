@@ -98,7 +98,8 @@ CONFIGS = {
 KERNEL_NAMES = {0: "ros_generic_kernel (table-driven, one cell per lane, workspace in HBM)",
                 1: "ros_smem_kernel<mech> (shared-memory Rodas3 integrator, one launch per step)",
                 2: "ros_warp_kernel<mech> (warp-group shared-memory Rodas3 integrator)",
-                3: "ros_lane_kernel (one cell per lane, streamed workspace)"}
+                3: "ros_lane_kernel (one cell per lane, streamed workspace)",
+                4: "ros_unrolled_kernel<mech> (one cell per thread, generated straight-line code)"}
 
 
 def resolve(args, world):

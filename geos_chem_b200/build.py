@@ -31,6 +31,8 @@ UNITS = {
     "ros_warp.cu": (["-DWARP_PROFILE"] if os.environ.get("GCKPP_WARP_PROFILE") else []) + os.environ.get("GCKPP_WARP_DEFS", "").split(),
     # Do_FullChem's pieces around the integration, reference operation order
     "post.cu": ["-fmad=false"],
+    # one cell per thread, generated straight-line code (small mechanisms)
+    "ros_unrolled.cu": os.environ.get("GCKPP_UNR_DEFS", "").split(),
     # one cell per lane, streamed workspace
     "ros_lane.cu": (["-DLANE_PROFILE"] if os.environ.get("GCKPP_LANE_PROFILE") else []) + os.environ.get("GCKPP_LANE_DEFS", "").split(),
     "gckpp_gpu.cu": os.environ.get("GCKPP_SMEM_DEFS", "").split() + os.environ.get("GCKPP_WARP_DEFS", "").split(),

@@ -598,6 +598,8 @@ static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
   if (h->opt_kernel == 3) return host_lsched(h->mech_id) ? 3 : 0;     // lane kernel: every method
   // small mechanisms (Hg: 32 species, 161 matrix entries): the lane kernel is the default -- a warp's whole
   // workspace is 150 KB, seven warps fit an SM, 2.7 M cells/s against 1.1 M for the block kernel (profiles/r02r_hg_bench.log)
+  if (h->opt_kernel == 4) return unrolled_kernel_supports(h->mech_id) ? 4 : 0;
+  if (h->opt_kernel < 0 && unrolled_kernel_supports(h->mech_id)) return 4;      // one cell per thread, straight-line code
   if (h->opt_kernel < 0 && h->T->nvar <= 64 && host_lsched(h->mech_id)) return 3;
   if (!(d.ICNTRL[2] == 0 || d.ICNTRL[2] == 4)) return 0;
   if (d.o.Tstart == d.o.Tend) return 0;
@@ -617,7 +619,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   const bool smem = kern == 1;
   int blocks = (nwork + h->threads - 1) / h->threads;
   if (blocks > h->max_blocks) blocks = h->max_blocks;
-  int rc = kern == 3 ? prepare_lane(h) : kern == 2 ? prepare_warp(h) : (smem ? prepare_smem(h) : ensure_workspace(h, blocks));
+  int rc = kern == 4 ? 0 : kern == 3 ? prepare_lane(h) : kern == 2 ? prepare_warp(h) : (smem ? prepare_smem(h) : ensure_workspace(h, blocks));
   if (rc) return rc;
   RosArgs a;
   a.ncell = ncell; a.nwork = nwork; a.cell_list = cell_list;
@@ -635,6 +637,12 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
   CUDA_TRY(cudaMemsetAsync(h->next.p, 0, sizeof(int), h->stream));
   if (h->T->nnz == 0) {   // carbon: forward Euler
     CUDA_TRY(launch_feuler(h->M, a, d.ICNTRL[15], h->stream));
+  } else if (kern == 4) { // one cell per thread, persistent lanes
+    const int bt = unrolled_block_threads();
+    int nb = (nwork + bt - 1) / bt;
+    if (nb > h->sm_count * unrolled_blocks_per_sm()) nb = h->sm_count * unrolled_blocks_per_sm();
+    CUDA_TRY(launch_ros_unrolled(h->mech_id, a, nb, h->stream));
+    h->last_kernel = 4;
   } else if (kern == 3) { // one cell per lane, one warp per block, persistent
     int nb = (nwork + 31) / 32;
     if (nb > h->l_blocks) nb = h->l_blocks;

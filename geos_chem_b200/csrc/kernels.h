@@ -33,3 +33,9 @@ cudaError_t launch_post_integrate(double *conc, int ncell, int nspec, const int 
 cudaError_t launch_prod_loss(const double *conc, int ncell, double dt, const int *ids, int nslots, double *out, cudaStream_t s);
 cudaError_t launch_oh_reactivity(const double *conc, const double *rconst, int ncell, const double *coef, const int *rxn,
                                  const int *spc, int nterms, double *out, cudaStream_t s);
+
+// ros_unrolled.cu: one cell per thread, generated straight-line code (small mechanisms)
+bool unrolled_kernel_supports(int mech_id);
+int unrolled_block_threads();
+int unrolled_blocks_per_sm();
+cudaError_t launch_ros_unrolled(int mech_id, const RosArgs &a, int blocks, cudaStream_t s);

@@ -1,4 +1,5 @@
 #!/bin/bash
-o=gpurun_out/r02w; mkdir -p $o
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --config 4 --steps 1 --warmup 1 ) > $o/bench_c180_n8.log 2>&1; grep "^{" $o/bench_c180_n8.log | cut -c1-900; tail -3 $o/bench_c180_n8.log | cut -c1-200
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --steps 2 --warmup 3 ) > $o/bench_n8.log 2>&1; grep "^{" $o/bench_n8.log | cut -c1-600
+o=gpurun_out/r02y; mkdir -p $o
+for v in _u4 _u6 _u8; do ( GCKPP_B200_LIB=geos_chem_b200/libgckpp_b200$v.so timeout 300 python bench.py --config 5-hg --steps 5 --warmup 3 --no-cpu-baseline ) 2>&1 | grep "^{" | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print('variant $v', d['value'], d['e2e']['value'], d['roofline']['kernel_ms'])" | tee -a $o/hg_variants.log; done
