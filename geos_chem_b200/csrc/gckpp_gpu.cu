@@ -138,6 +138,10 @@ struct gckpp_gpu_handle {
   DevBuf l_tab[7], l_lit, l_ws;
   const double *ohr_coef = nullptr; const int *ohr_rxn = nullptr, *ohr_spc = nullptr;   // Get_OHreactivity terms (device)
   DevBuf small;                            // the little index lists of the post-integrate entry points
+  // heterogeneous laws on the device: SR_MW (device copy), the caller's HetState fields and, for the stand-alone
+  // Update_RCONST entry points, its concentrations (host or device pointers, whatever the next call takes)
+  DevBuf srmw; int srmw_n = 0;
+  const double *het_user = nullptr, *het_conc_user = nullptr;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -260,7 +264,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->s_active, &h->s_ist, &h->s_rst, &h->s_ierr,
                     &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
                     &h->l_tab[0], &h->l_tab[1], &h->l_tab[2], &h->l_tab[3], &h->l_tab[4], &h->l_tab[5], &h->l_tab[6], &h->l_lit, &h->l_ws,
-                    &h->small,
+                    &h->small, &h->srmw,
                     &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
   for (DevBuf *b : bufs) b->release();
   free_slots(h);
@@ -673,6 +677,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
 // The arrays of one call (or one wave of a call) on the device; every per-cell array has row stride n.
 struct DevIO {
   const double *conc_in, *rconst, *temp, *numden, *h2o, *photol, *khet, *hstart;
+  const double *het;          // [GCKPP_NHET][n] HetState fields for the device-side heterogeneous laws, or NULL
   const uint8_t *active;
   double *conc_out; int32_t *istatus; double *rstatus; int32_t *ierr;
   double *rconst_work;        // [NREACT][n] scratch for Update_RCONST when rconst == NULL
@@ -720,8 +725,10 @@ static int device_core(gckpp_gpu_handle *h, const Decoded &d, int n, const DevIO
     int rc_stride = n, rc_cell0 = 0;
     if (!rconst) {
       CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+      const bool dohet = io.het && h->srmw_n > 0;
       CUDA_TRY(launch_update_rconst(h->mech_id, m, io.temp + c0, io.numden + c0, io.h2o + c0, io.photol ? io.photol + c0 : nullptr,
-                                    io.khet ? io.khet + c0 : nullptr, io.rconst_work, h->stream, /*input stride*/ n, /*output stride*/ m));
+                                    io.khet ? io.khet + c0 : nullptr, io.rconst_work, h->stream, /*input stride*/ n, /*output stride*/ m,
+                                    dohet ? io.het + c0 : nullptr, dohet ? io.conc_in + c0 : nullptr, dohet ? h->srmw.as<double>() : nullptr));
       CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
       h->stats[6] += 1;
       h->stats[12] += 1;          // Update_RCONST launches of this call
@@ -832,7 +839,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     const size_t dw = (size_t)(h->opt_dev_wave > 0 ? h->opt_dev_wave : (1 << 20));
     if (!rconst && h->rconst_work.ensure(sizeof(double) * (size_t)T->nreact * ((size_t)ncell < dw ? (size_t)ncell : dw))) return fail(-1002, "out of device memory for rconst");
   }
-  DevIO io{conc_in, rconst, temp, numden, h2o, photol, khet, hstart, active, conc_out, istatus, rstatus, ierr,
+  DevIO io{conc_in, rconst, temp, numden, h2o, photol, khet, hstart, h->het_user, active, conc_out, istatus, rstatus, ierr,
            h->rconst_work.as<double>()};
   CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
   unsigned long long fails = 0;
@@ -853,7 +860,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
 // copy-out stream.  This is the batched replacement of the cell loop of Do_FullChem (fullchem_mod.F90:528-1551): one
 // call per chemistry step per GPU, as GCHP calls the routine once per tile (gchp_chunk_mod.F90:1366).
 struct WaveSlot {
-  DevBuf conc_in, conc_out, rconst, met, photol, khet, hstart, active, ist, rst, ierr;
+  DevBuf conc_in, conc_out, rconst, met, photol, khet, het, hstart, active, ist, rst, ierr;
   cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
 };
 
@@ -876,7 +883,7 @@ static void free_slots(gckpp_gpu_handle *h)
   if (!h->slots) return;
   for (int i = 0; i < 2; i++) {
     WaveSlot &s = h->slots[i];
-    DevBuf *b[] = {&s.conc_in, &s.conc_out, &s.rconst, &s.met, &s.photol, &s.khet, &s.hstart, &s.active, &s.ist, &s.rst, &s.ierr};
+    DevBuf *b[] = {&s.conc_in, &s.conc_out, &s.rconst, &s.met, &s.photol, &s.khet, &s.het, &s.hstart, &s.active, &s.ist, &s.rst, &s.ierr};
     for (DevBuf *x : b) x->release();
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -924,6 +931,7 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
   if ((rc = ensure_slots(h))) return rc;
   for (int i = 0; i < 16; i++) h->stats[i] = 0.0;
   const bool have_met = temp && numden && h2o, have_ph = photol && T->nphot, have_kh = khet && T->next;
+  const double *het = (h->srmw_n > 0 && !rconst) ? h->het_user : nullptr;      // HetState fields (host array) for the device-side laws
   // wave size: "wave_cells" (default 65536), or ncell / "chunks" when that option was set explicitly
   size_t W = (size_t)(h->opt_wave_cells > 0 ? h->opt_wave_cells : 65536);
   if (h->opt_chunks > 0) W = (nc + h->opt_chunks - 1) / h->opt_chunks;
@@ -938,6 +946,7 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
     if (have_ph) pins.add(photol, 8 * T->nphot * nc);
     if (have_kh) pins.add(khet, 8 * T->next * nc);
     if (hstart) pins.add(hstart, 8 * nc);
+    if (het) pins.add(het, 8 * (size_t)GCKPP_NHET * nc);
     if (istatus) pins.add(istatus, 4 * 8 * nc);
     if (rstatus) pins.add(rstatus, 8 * 4 * nc);
     if (ierr) pins.add(ierr, 4 * nc);
@@ -947,7 +956,8 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
     if (s.conc_in.ensure(8 * T->nspec * W) || s.conc_out.ensure(8 * T->nspec * W) || s.ist.ensure(4 * 8 * W) ||
         s.rst.ensure(8 * 4 * W) || s.ierr.ensure(4 * W) || s.rconst.ensure(8 * T->nreact * W) ||
         (have_met && s.met.ensure(3 * 8 * W)) || (hstart && s.hstart.ensure(8 * W)) || (active && s.active.ensure(W)) ||
-        (have_ph && s.photol.ensure(8 * T->nphot * W)) || (have_kh && s.khet.ensure(8 * T->next * W)))
+        (have_ph && s.photol.ensure(8 * T->nphot * W)) || (have_kh && s.khet.ensure(8 * T->next * W)) ||
+        (het && s.het.ensure(8 * (size_t)GCKPP_NHET * W)))
       return fail(-1002, "out of device memory for a wave of %zu cells", W);
   }
   CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
@@ -972,6 +982,7 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
     }
     if (have_ph) CUDA_TRY(rows_in(s.photol.p, photol, c0, n, T->nphot, 8));
     if (have_kh) CUDA_TRY(rows_in(s.khet.p, khet, c0, n, T->next, 8));
+    if (het) CUDA_TRY(rows_in(s.het.p, het, c0, n, GCKPP_NHET, 8));
     if (hstart) CUDA_TRY(rows_in(s.hstart.p, hstart, c0, n, 1, 8));
     if (active) CUDA_TRY(rows_in(s.active.p, active, c0, n, 1, 1));
     CUDA_TRY(cudaEventRecord(s.ev_in, h->s_in));
@@ -988,7 +999,8 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
     double *m = s.met.as<double>();
     DevIO io{s.conc_in.as<double>(), rconst ? s.rconst.as<double>() : nullptr, have_met ? m : nullptr, have_met ? m + n : nullptr,
              have_met ? m + 2 * n : nullptr, have_ph ? s.photol.as<double>() : nullptr, have_kh ? s.khet.as<double>() : nullptr,
-             hstart ? s.hstart.as<double>() : nullptr, active ? s.active.as<uint8_t>() : nullptr, s.conc_out.as<double>(),
+             hstart ? s.hstart.as<double>() : nullptr, het ? s.het.as<double>() : nullptr,
+             active ? s.active.as<uint8_t>() : nullptr, s.conc_out.as<double>(),
              s.ist.as<int32_t>(), s.rst.as<double>(), s.ierr.as<int32_t>(), s.rconst.as<double>()};
     if ((rc = device_core(h, d, (int)n, io, &fails))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev_done, h->stream));
@@ -1015,6 +1027,29 @@ static int h2d(gckpp_gpu_handle *h, DevBuf &b, const void *src, size_t bytes)
   return 0;
 }
 
+// ---- heterogeneous laws on the device ---------------------------------------------------------------------
+extern "C" int gckpp_gpu_set_sr_mw(gckpp_gpu_handle_t *h, int n, const double *sr_mw)
+{
+  if (!h || n < 0 || (n > 0 && !sr_mw)) return fail(-10, "gckpp_gpu_set_sr_mw: bad arguments");
+  if (n != 0 && n != h->T->nspec) return fail(-10, "gckpp_gpu_set_sr_mw: expected %d values (one per species)", h->T->nspec);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (n > 0) {
+    if (h->srmw.ensure(sizeof(double) * (size_t)n)) return fail(-1002, "out of device memory");
+    CUDA_TRY(cudaMemcpy(h->srmw.p, sr_mw, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  }
+  h->srmw_n = n;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_set_het(gckpp_gpu_handle_t *h, const double *het, const double *conc)
+{
+  if (!h) return fail(-10, "NULL handle");
+  if (het && h->mech_id != GCKPP_MECH_FULLCHEM) return fail(-11, "device-side heterogeneous laws exist for fullchem only");
+  if (het && h->srmw_n == 0) return fail(-10, "gckpp_gpu_set_het: call gckpp_gpu_set_sr_mw first");
+  h->het_user = het; h->het_conc_user = het ? conc : nullptr;
+  return 0;
+}
+
 extern "C" int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *h, int ncell,
                                               const double *temp, const double *numden, const double *h2o,
                                               const double *photol, const double *khet, double *rconst_out)
@@ -1022,7 +1057,9 @@ extern "C" int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *h, int ncell,
   if (!h || !temp || !numden || !h2o || !rconst_out || ncell < 0) return fail(-10, "gckpp_gpu_update_rconst: bad arguments");
   if (ncell == 0) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, rconst_out, h->stream));
+  const bool dohet = h->het_user && h->het_conc_user && h->srmw_n > 0;        // both device pointers here
+  CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, rconst_out, h->stream, 0, 0,
+                                dohet ? h->het_user : nullptr, dohet ? h->het_conc_user : nullptr, dohet ? h->srmw.as<double>() : nullptr));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1045,9 +1082,14 @@ extern "C" int gckpp_gpu_update_rconst(gckpp_gpu_handle_t *h, int ncell,
   if (photol && T->nphot && (rc = h2d(h, h->s_photol, photol, sizeof(double) * T->nphot * nc))) return rc;
   if (khet && T->next && (rc = h2d(h, h->s_khet, khet, sizeof(double) * T->next * nc))) return rc;
   if (h->s_rconst.ensure(sizeof(double) * T->nreact * nc)) return fail(-1002, "out of device memory");
+  const bool dohet = h->het_user && h->het_conc_user && h->srmw_n > 0;        // both host arrays here: staged
+  if (dohet && ((rc = h2d(h, h->s_conc_in, h->het_conc_user, sizeof(double) * T->nspec * nc)) ||
+                (rc = h2d(h, h->s_conc_out, h->het_user, sizeof(double) * (size_t)GCKPP_NHET * nc)))) return rc;
   CUDA_TRY(launch_update_rconst(h->mech_id, ncell, d_temp, d_numden, d_h2o,
                                 (photol && T->nphot) ? h->s_photol.as<double>() : nullptr,
-                                (khet && T->next) ? h->s_khet.as<double>() : nullptr, h->s_rconst.as<double>(), h->stream));
+                                (khet && T->next) ? h->s_khet.as<double>() : nullptr, h->s_rconst.as<double>(), h->stream, 0, 0,
+                                dohet ? h->s_conc_out.as<double>() : nullptr, dohet ? h->s_conc_in.as<double>() : nullptr,
+                                dohet ? h->srmw.as<double>() : nullptr));
   CUDA_TRY(cudaMemcpyAsync(rconst_out, h->s_rconst.p, sizeof(double) * T->nreact * nc, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;

@@ -5,6 +5,7 @@
 //   select_failed_kernel  <- the IERR<0 retry list (fullchem_mod.F90:1138)
 #include "kernels.h"
 #include "ratelaws.cuh"
+#include "hetlaws.cuh"
 #include "gen/fullchem_rconst.cuh"
 #include "gen/Hg_rconst.cuh"
 #include "gen/carbon_rconst.cuh"
@@ -19,13 +20,22 @@ __device__ __forceinline__ MetCell make_met(double temp, double numden, double h
   m.TEMP_OVER_K300 = temp / 300.0;
   m.K300_OVER_TEMP = 300.0 / temp;
   m.SR_TEMP = sqrt(temp);
+  // the rest of Set_Kpp_GridBox_Values (fullchem_mod.F90:2145-2160; constants of Headers/physconstants.F90 and
+  // commonIncludeVars.H:7): CON_R, RGASLATM, RSTARG, CONSVAP = 6.1078e3 / (BOLTZ * 1e7)
+  m.FOUR_R_T = 4.0 * 0.083144598 * temp;
+  m.FOUR_RGASLATM_T = 4.0 * 8.2057e-2 * temp;
+  m.EIGHT_RSTARG_T = 8.0 * 8.3144598 * temp;
+  const double consexp = 17.2693882 * (temp - 273.16) / (temp - 35.86);
+  const double vpresh2o = (6.1078e+03 / (1.38064852e-23 * 1e+7)) * exp(consexp) / temp;
+  m.RELHUM = (h2o / vpresh2o) * 100.0;
   return m;
 }
 
 template <int MECH>
 __global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int stride, int ostride, const double *__restrict__ temp,
     const double *__restrict__ numden, const double *__restrict__ h2o, const double *__restrict__ photol,
-    const double *__restrict__ khet, double *__restrict__ rconst)
+    const double *__restrict__ khet, double *__restrict__ rconst, const double *__restrict__ het,
+    const double *__restrict__ conc, const double *__restrict__ srmw)
 {
   // ncell cells starting at the given pointers; rows of the cell-fastest input arrays are `stride` apart, rows of
   // rconst `ostride`
@@ -34,9 +44,13 @@ __global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int strid
   MetCell m = make_met(temp[cell], numden[cell], h2o[cell]);
   const double *ph = photol ? photol + cell : nullptr;
   const double *kh = khet ? khet + cell : nullptr;
-  if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
-  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
-  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride);
+  // heterogeneous laws on the device (fullchem, when the caller supplies the HetState fields): see hetlaws.cuh
+  if (MECH == 0 && het && conc && srmw) {
+    const HetCell H = het_load(het + cell, (size_t)stride);
+    fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw);
+  } else if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
+  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
+  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
 }
 
 __global__ void fill_int_kernel(int *p, int n, int v)
@@ -121,14 +135,15 @@ cudaError_t measure_fp64_peak(double *tflops, double *ms_out)
 
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,
-                                 double *rconst, cudaStream_t s, int stride, int ostride)
+                                 double *rconst, cudaStream_t s, int stride, int ostride,
+                                 const double *het, const double *conc, const double *srmw)
 {
   int blocks = (ncell + 127) / 128;
   if (stride <= 0) stride = ncell;
   if (ostride <= 0) ostride = stride;
-  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
-  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
-  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst);
+  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
+  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
+  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
   return cudaGetLastError();
 }
 __global__ void iota_kernel(int *p, int n)

@@ -46,4 +46,5 @@ struct MechDev {
 struct MetCell {
   double TEMP, NUMDEN, H2O;
   double INV_TEMP, TEMP_OVER_K300, K300_OVER_TEMP, SR_TEMP;
+  double FOUR_R_T, FOUR_RGASLATM_T, EIGHT_RSTARG_T, RELHUM;     // :2145-2160, read by the heterogeneous laws
 };

@@ -67,6 +67,8 @@ def load_library(path=None):
     L.gckpp_gpu_plan_info.argtypes = [C.c_int, ip]
     L.gckpp_gpu_set_keep_active.argtypes = [vp, C.c_int, ip]
     L.gckpp_gpu_warp_plan.argtypes = [C.c_int, ip, C.c_int, vp, C.c_int64]
+    L.gckpp_gpu_set_sr_mw.argtypes = [vp, C.c_int, vp]
+    L.gckpp_gpu_set_het.argtypes = [vp, vp, vp]
     for sfx in ("", "_device"):
         getattr(L, "gckpp_gpu_zero_species" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp]
         getattr(L, "gckpp_gpu_post_integrate" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
@@ -83,7 +85,7 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active", "gckpp_gpu_warp_plan",
            "gckpp_gpu_zero_species", "gckpp_gpu_zero_species_device", "gckpp_gpu_post_integrate",
            "gckpp_gpu_post_integrate_device", "gckpp_gpu_prod_loss", "gckpp_gpu_prod_loss_device",
-           "gckpp_gpu_oh_reactivity", "gckpp_gpu_oh_reactivity_device"]
+           "gckpp_gpu_oh_reactivity", "gckpp_gpu_oh_reactivity_device", "gckpp_gpu_set_sr_mw", "gckpp_gpu_set_het"]
 
 
 def plan_info(mech):
@@ -325,6 +327,33 @@ class KppSolver:
         x = _np(X, np.float64).copy()
         self._check(self.L.gckpp_gpu_solve(self.h, j.shape[1], _ptr(j), _ptr(x)), "KppSolve")
         return x
+
+    # ------------------------------------------------------------------ heterogeneous laws on the device
+    NHET = 48
+    HET_FIELDS = ("SUNCOS", "stratBox", "SSA_is_Alk", "SSA_is_Acid", "SSC_is_Alk", "SSC_is_Acid", "f_Alk_SSA", "f_Alk_SSC",
+                  "f_Acid_SSA", "f_Acid_SSC", "ClearFr", "aClArea", "aClRadi", "Cl_conc_SSA", "Cl_conc_SSC", "gamma_HO2",
+                  "H_PLUS", "NO3_molal", "SO4_molal", "HSO4_molal") + tuple("xArea%d" % k for k in range(1, 15)) + \
+        tuple("xRadi%d" % k for k in range(1, 15))
+
+    def set_sr_mw(self, sr_mw):
+        """SR_MW(1:NSPEC) of gckpp_Global (SQRT of the molecular weights); None switches the device-side laws off"""
+        if sr_mw is None:
+            self._check(self.L.gckpp_gpu_set_sr_mw(self.h, 0, None), "set_sr_mw")
+            return
+        a = _np(sr_mw, np.float64, (self.dims["nspec"],), "sr_mw")
+        self._check(self.L.gckpp_gpu_set_sr_mw(self.h, a.size, _ptr(a)), "set_sr_mw")
+
+    def set_het(self, het, conc=None):
+        """HetState fields [NHET, ncell] (order: HET_FIELDS) for the next calls; numpy for the host entry points, a CUDA
+        tensor for the device ones; None = off.  The arrays must stay alive until those calls have been made."""
+        self._het_keep = (het, conc)
+        if het is not None and not _is_torch(het):
+            het = _np(het, np.float64)
+            conc = None if conc is None else _np(conc, np.float64)
+            self._het_keep = (het, conc)
+        if het is not None and het.shape[0] != self.NHET:
+            raise ValueError("het: expected [%d, ncell]" % self.NHET)
+        self._check(self.L.gckpp_gpu_set_het(self.h, _ptr(het), _ptr(conc)), "set_het")
 
     # ------------------------------------------------------------------ Do_FullChem's pieces around the integration
     # numpy arrays are staged through the host entry points (a new array is returned), torch CUDA tensors are

@@ -118,6 +118,29 @@ int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *handle, int ncell,
                                    const double *temp, const double *numden, const double *h2o,
                                    const double *photol, const double *khet, double *rconst_out);
 
+/* Heterogeneous rate laws on the device (fullchem; SURVEY 8 f1, first part).  Without these calls every externally
+ * supplied constant comes from khet, as before.  With them, Update_RCONST -- inside gckpp_gpu_integrate[_device] and in
+ * the stand-alone entry points -- evaluates 61 of the 113 itself (KPP/fullchem/fullchem_RateLawFuncs.F90: VOCuptk1stOrd,
+ * IEPOXuptk1stOrd, MGLYuptk1stOrd, GLYXuptk1stOrd :3286-3458; Iuptk* / IbrkdnByAcid* :2371-2542; HO2uptk1stOrd :1461-1484;
+ * HBrUptkBySALA/SALC :1423-1455; OHuptkBySALACl/SALCCl :3244-3280; utilities rateLawUtilFuncs.F90:77-140, 459-495) and
+ * takes only the remaining ones (K_MT, K_CLD, cloud / halogen / N2O5 / NO2 / NO3 laws) from khet.
+ *   set_sr_mw   SR_MW(1:NSPEC) = SQRT(MW) of gckpp_Global (filled by the host from the species database); n = NSPEC, or 0 = off
+ *   set_het     het[GCKPP_NHET][ncell], cell-fastest, the HetState fields below (commonIncludeVars.H:112-210; logicals as
+ *               0.0 / 1.0) for the cells of the NEXT calls: a host array for the host entry points, a device array for the
+ *               _device ones; NULL = off.  conc: the concentrations the laws read, needed only by the stand-alone
+ *               gckpp_gpu_update_rconst[_device] (the integrate entry points use their own conc_in). */
+enum {
+  GCKPP_HET_SUNCOS = 0, GCKPP_HET_STRATBOX, GCKPP_HET_SSA_IS_ALK, GCKPP_HET_SSA_IS_ACID, GCKPP_HET_SSC_IS_ALK,
+  GCKPP_HET_SSC_IS_ACID, GCKPP_HET_F_ALK_SSA, GCKPP_HET_F_ALK_SSC, GCKPP_HET_F_ACID_SSA, GCKPP_HET_F_ACID_SSC,
+  GCKPP_HET_CLEARFR, GCKPP_HET_ACLAREA, GCKPP_HET_ACLRADI, GCKPP_HET_CL_CONC_SSA, GCKPP_HET_CL_CONC_SSC,
+  GCKPP_HET_GAMMA_HO2, GCKPP_HET_H_PLUS, GCKPP_HET_NO3_MOLAL, GCKPP_HET_SO4_MOLAL, GCKPP_HET_HSO4_MOLAL,
+  GCKPP_HET_XAREA = 20,   /* xArea(1:14): DU1..DU7, SUL, BKC, ORC, SSA, SSC, SLA, IIC */
+  GCKPP_HET_XRADI = 34,   /* xRadi(1:14) */
+  GCKPP_NHET = 48
+};
+int gckpp_gpu_set_sr_mw(gckpp_gpu_handle_t *handle, int n, const double *sr_mw);
+int gckpp_gpu_set_het(gckpp_gpu_handle_t *handle, const double *het, const double *conc);
+
 /* Fun(V,F,RCT,Vdot,Aout) over cells (RxnRate diagnostics, fullchem_mod.F90:967-992):
  * vdot [NVAR][ncell] and aout [NREACT][ncell]; either output may be NULL.  Host pointers. */
 int gckpp_gpu_fun(gckpp_gpu_handle_t *handle, int ncell, const double *conc, const double *rconst,

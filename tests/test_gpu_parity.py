@@ -473,3 +473,79 @@ def test_post_integrate_pieces_vs_oracle(solver, oracle):
     assert np.array_equal(toh.cpu().numpy(), oho)
     tpl = solver.prod_loss(tc, 1200.0, fam)
     assert np.array_equal(tpl.cpu().numpy(), po.prod_loss(c2, 1200.0, fam))
+
+
+def test_heterogeneous_laws_on_device_vs_oracle(solver, oracle):
+    """SURVEY 8 f1, first part: with SR_MW and the HetState fields supplied, Update_RCONST evaluates 61 of the 113
+    externally supplied constants itself (csrc/hetlaws.cuh); the others keep coming from khet.  GPU against the scalar
+    Python restatement of the Fortran (oracle/het_oracle.py), 1e-12 relative; through the stand-alone entry point and
+    inside Integrate (host entry in waves, and device entry).  Parity unpinned by the reference."""
+    import torch
+    from oracle import het_oracle as ho
+    from geos_chem_b200.kppgen import ir
+    m = ir.load("fullchem")
+    n = 403
+    g = grid.make_grid("4x5", limit=30000)
+    rng = np.random.default_rng(41)
+    idx = np.sort(rng.choice(30000, n, replace=False))
+    sub = lambda a: np.ascontiguousarray(a[..., idx])
+    temp, numden, h2o, photol, khet, conc, hs = map(sub, (g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"], g["conc"], g["hstart"]))
+    F = kpp.KppSolver.HET_FIELDS
+    het = np.zeros((kpp.KppSolver.NHET, n))
+    col = {name: k for k, name in enumerate(F)}
+    het[col["SUNCOS"]] = rng.uniform(-0.5, 1.0, n)
+    for flag in ("stratBox", "SSA_is_Alk", "SSA_is_Acid", "SSC_is_Alk", "SSC_is_Acid"):
+        het[col[flag]] = (rng.uniform(size=n) < 0.4).astype(np.float64)
+    for fr in ("f_Alk_SSA", "f_Alk_SSC", "f_Acid_SSA", "f_Acid_SSC", "ClearFr"):
+        het[col[fr]] = rng.uniform(0.0, 1.0, n)
+    het[col["aClArea"]] = 10 ** rng.uniform(-9, -6, n); het[col["aClRadi"]] = 10 ** rng.uniform(-6, -4, n)
+    het[col["Cl_conc_SSA"]] = 10 ** rng.uniform(-2, 1, n); het[col["Cl_conc_SSC"]] = 10 ** rng.uniform(-2, 1, n)
+    het[col["gamma_HO2"]] = rng.uniform(0.0, 0.3, n)
+    het[col["H_PLUS"]] = 10 ** rng.uniform(-6, -2, n)
+    for mol in ("NO3_molal", "SO4_molal", "HSO4_molal"):
+        het[col[mol]] = 10 ** rng.uniform(-3, 1, n)
+    for k in range(1, 15):
+        het[col["xArea%d" % k]] = np.where(rng.uniform(size=n) < 0.15, 0.0, 10 ** rng.uniform(-10, -6, n))
+        het[col["xRadi%d" % k]] = 10 ** rng.uniform(-6.5, -3.5, n)
+    h2o = h2o * 10 ** rng.uniform(-0.5, 1.0, n)            # relative humidities on both sides of CRITRH
+    sr_mw = np.sqrt(rng.uniform(17.0, 300.0, m.nspec))
+    want = [ho.evaluate(m.rconst, m.ind, ho.Cell(temp[c], numden[c], h2o[c], het[:, c], sr_mw, conc[:, c], F)) for c in range(n)]
+    rows = sorted(want[0])
+    assert len(rows) == 61
+    ref = oracle.update_rconst("fullchem", temp, numden, h2o, photol, khet)
+    exp = ref.copy()
+    for c in range(n):
+        for r in rows:
+            exp[r, c] = want[c][r]
+    assert (exp[rows] != ref[rows]).mean() > 0.5 and (exp[rows] > 0).mean() > 0.2
+    solver.set_sr_mw(sr_mw)
+    try:
+        solver.set_het(het, conc)
+        rc = solver.Update_RCONST(temp, numden, h2o, photol, khet)
+        others = np.setdiff1d(np.arange(m.nreact), rows)
+        plain = solver_plain_rconst = None
+        err = np.abs(rc[rows] - exp[rows]) / np.maximum(np.abs(exp[rows]), 1e-300)
+        print("device het laws: max rel err %.2e over %d constants x %d cells" % (err.max(), len(rows), n))
+        assert err.max() <= 1e-12
+        solver.set_het(None)
+        rc0 = solver.Update_RCONST(temp, numden, h2o, photol, khet)
+        assert np.array_equal(rc[others], rc0[others]) and np.array_equal(rc0[rows], ref[rows])
+        # inside Integrate: the call with het must equal the call that is handed the same constants through RCONST
+        solver.set_option("kernel", 1)
+        c_ref, i_ref, _, e_ref, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs)
+        solver.set_het(het)
+        solver.set_option("wave_cells", 128)
+        c1, i1, _, e1, _ = solver.Integrate(0.0, 1200.0, conc, None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs,
+                                            TEMP=temp, NUMDEN=numden, H2O=h2o, PHOTOL=photol, khet=khet)
+        assert np.array_equal(c1, c_ref) and np.array_equal(i1, i_ref) and np.array_equal(e1, e_ref)
+        dev = torch.device("cuda", 0)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        thet = T(het)
+        solver.set_het(thet)
+        c2, i2, _, e2, _ = solver.Integrate(0.0, 1200.0, T(conc), None, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=T(hs),
+                                            TEMP=T(temp), NUMDEN=T(numden), H2O=T(h2o), PHOTOL=T(photol), khet=T(khet))
+        assert np.array_equal(c2.cpu().numpy(), c_ref) and np.array_equal(i2.cpu().numpy(), i_ref)
+    finally:
+        solver.set_option("wave_cells", 0)
+        solver.set_het(None)
+        solver.set_sr_mw(None)
