@@ -214,6 +214,9 @@ def run_reference(args, rank, world):
     save = (args.shard_of, args.shard_rank)
     args.shard_of, args.shard_rank = (1, 0) if not args.shard_of else save
     g, shape = make_inputs(args, 0, 1)
+    from geos_chem_b200 import grid as _grid
+    # the B200 arm's own description of the workload (cells per GPU = rank 0's shard), so that the two lines name the same config
+    per_gpu = g["conc"].shape[1] if args.scaling == "weak" or args.cells else _grid.column_shard(shape, 0, max(args.gpus, 1)).shape[0]
     cores = host_cores()      # explicit: torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm
     o = pick_oracle(args, g, cores)
     warm = min(args.warmup, 1)
@@ -230,7 +233,7 @@ def run_reference(args, rank, world):
             "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, g["conc"].shape[1], args.gpus), "name": args.config, "sample": sample},
+            "config": {"workload": workload_name(args, per_gpu, args.gpus), "name": args.config, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
                              "build": o.build_desc,
                              "note": "C/OpenMP restatement of the reference algorithm, not gfortran/ifort output"},
