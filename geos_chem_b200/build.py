@@ -22,7 +22,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 
 # translation unit -> extra flags
 UNITS = {
-    "kernels_misc.cu": [],
+    # Update_RCONST and the small kernels: no FMA contraction, so the rate laws round operation by operation like the
+    # reference's expressions (the uptake laws contain cancellations that amplify a fused rounding); 0.1 % of a step
+    "kernels_misc.cu": ["-fmad=false"],
     # arithmetic-reference kernel: no FMA contraction so sums round like the reference's
     "ros_generic.cu": ["-fmad=false"],
     # production kernel: shared-memory-resident, FMA allowed

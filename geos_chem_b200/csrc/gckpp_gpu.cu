@@ -140,7 +140,7 @@ struct gckpp_gpu_handle {
   DevBuf small;                            // the little index lists of the post-integrate entry points
   // heterogeneous laws on the device: SR_MW (device copy), the caller's HetState fields and, for the stand-alone
   // Update_RCONST entry points, its concentrations (host or device pointers, whatever the next call takes)
-  DevBuf srmw; int srmw_n = 0;
+  DevBuf srmw; int srmw_n = 0, spc_data_n = 0;      // [SR_MW | MW | HENRY_K0 | HENRY_CR]
   const double *het_user = nullptr, *het_conc_user = nullptr;
   DevBuf keep_spc; int keep_n = 0;         // keepSpcActive of the auto-reduce solver
   // pipelined host entry: copy streams and the identity cell list
@@ -728,7 +728,8 @@ static int device_core(gckpp_gpu_handle *h, const Decoded &d, int n, const DevIO
       const bool dohet = io.het && h->srmw_n > 0;
       CUDA_TRY(launch_update_rconst(h->mech_id, m, io.temp + c0, io.numden + c0, io.h2o + c0, io.photol ? io.photol + c0 : nullptr,
                                     io.khet ? io.khet + c0 : nullptr, io.rconst_work, h->stream, /*input stride*/ n, /*output stride*/ m,
-                                    dohet ? io.het + c0 : nullptr, dohet ? io.conc_in + c0 : nullptr, dohet ? h->srmw.as<double>() : nullptr));
+                                    dohet ? io.het + c0 : nullptr, dohet ? io.conc_in + c0 : nullptr, dohet ? h->srmw.as<double>() : nullptr,
+                                    h->spc_data_n));
       CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
       h->stats[6] += 1;
       h->stats[12] += 1;          // Update_RCONST launches of this call
@@ -1034,10 +1035,24 @@ extern "C" int gckpp_gpu_set_sr_mw(gckpp_gpu_handle_t *h, int n, const double *s
   if (n != 0 && n != h->T->nspec) return fail(-10, "gckpp_gpu_set_sr_mw: expected %d values (one per species)", h->T->nspec);
   CUDA_TRY(cudaSetDevice(h->device));
   if (n > 0) {
-    if (h->srmw.ensure(sizeof(double) * (size_t)n)) return fail(-1002, "out of device memory");
+    if (h->srmw.ensure(sizeof(double) * 4 * (size_t)n)) return fail(-1002, "out of device memory");
     CUDA_TRY(cudaMemcpy(h->srmw.p, sr_mw, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   }
   h->srmw_n = n;
+  h->spc_data_n = 0;
+  return 0;
+}
+
+extern "C" int gckpp_gpu_set_species_data(gckpp_gpu_handle_t *h, int n, const double *sr_mw, const double *mw,
+                                          const double *henry_k0, const double *henry_cr)
+{
+  if (!h || !sr_mw || !mw || !henry_k0 || !henry_cr) return fail(-10, "gckpp_gpu_set_species_data: bad arguments");
+  int rc = gckpp_gpu_set_sr_mw(h, n, sr_mw);
+  if (rc || n == 0) return rc;
+  const double *src[3] = {mw, henry_k0, henry_cr};
+  for (int k = 0; k < 3; k++)
+    CUDA_TRY(cudaMemcpy(h->srmw.as<double>() + (size_t)(k + 1) * n, src[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  h->spc_data_n = n;
   return 0;
 }
 
@@ -1059,7 +1074,8 @@ extern "C" int gckpp_gpu_update_rconst_device(gckpp_gpu_handle_t *h, int ncell,
   CUDA_TRY(cudaSetDevice(h->device));
   const bool dohet = h->het_user && h->het_conc_user && h->srmw_n > 0;        // both device pointers here
   CUDA_TRY(launch_update_rconst(h->mech_id, ncell, temp, numden, h2o, photol, khet, rconst_out, h->stream, 0, 0,
-                                dohet ? h->het_user : nullptr, dohet ? h->het_conc_user : nullptr, dohet ? h->srmw.as<double>() : nullptr));
+                                dohet ? h->het_user : nullptr, dohet ? h->het_conc_user : nullptr, dohet ? h->srmw.as<double>() : nullptr,
+                                h->spc_data_n));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1089,7 +1105,7 @@ extern "C" int gckpp_gpu_update_rconst(gckpp_gpu_handle_t *h, int ncell,
                                 (photol && T->nphot) ? h->s_photol.as<double>() : nullptr,
                                 (khet && T->next) ? h->s_khet.as<double>() : nullptr, h->s_rconst.as<double>(), h->stream, 0, 0,
                                 dohet ? h->s_conc_out.as<double>() : nullptr, dohet ? h->s_conc_in.as<double>() : nullptr,
-                                dohet ? h->srmw.as<double>() : nullptr));
+                                dohet ? h->srmw.as<double>() : nullptr, h->spc_data_n));
   CUDA_TRY(cudaMemcpyAsync(rconst_out, h->s_rconst.p, sizeof(double) * T->nreact * nc, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;

@@ -18,7 +18,8 @@ cudaError_t launch_solve_cells(const MechDev &M, int ncell, const double *jvs, d
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,
                                  double *rconst, cudaStream_t s, int stride = 0, int ostride = 0,
-                                 const double *het = nullptr, const double *conc = nullptr, const double *srmw = nullptr);
+                                 const double *het = nullptr, const double *conc = nullptr, const double *srmw = nullptr,
+                                 int nspec_data = 0);
 cudaError_t launch_iota(int *p, int n, cudaStream_t s);
 cudaError_t launch_fill_int(int *p, int n, int v, cudaStream_t s);
 cudaError_t launch_select_active(int ncell, int c0, int c1, const uint8_t *active, int nspec, const double *conc_in,

@@ -35,7 +35,7 @@ template <int MECH>
 __global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int stride, int ostride, const double *__restrict__ temp,
     const double *__restrict__ numden, const double *__restrict__ h2o, const double *__restrict__ photol,
     const double *__restrict__ khet, double *__restrict__ rconst, const double *__restrict__ het,
-    const double *__restrict__ conc, const double *__restrict__ srmw)
+    const double *__restrict__ conc, const double *__restrict__ srmw, int nspec_data)
 {
   // ncell cells starting at the given pointers; rows of the cell-fastest input arrays are `stride` apart, rows of
   // rconst `ostride`
@@ -45,12 +45,19 @@ __global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int strid
   const double *ph = photol ? photol + cell : nullptr;
   const double *kh = khet ? khet + cell : nullptr;
   // heterogeneous laws on the device (fullchem, when the caller supplies the HetState fields): see hetlaws.cuh
+  // srmw points at [SR_MW | MW | HENRY_K0 | HENRY_CR], nspec_data values each; the last three only when the host gave them
   if (MECH == 0 && het && conc && srmw) {
     const HetCell H = het_load(het + cell, (size_t)stride);
-    fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw);
-  } else if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
-  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
-  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr);
+    if (nspec_data > 0) {
+      const HetCell2 G = het_load2(het + cell, (size_t)stride);
+      const HetCtx X{m, H, G, srmw, srmw + nspec_data, srmw + 2 * nspec_data, srmw + 3 * nspec_data, conc + cell, (size_t)stride};
+      fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw, &X);
+    } else {
+      fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw, nullptr);
+    }
+  } else if (MECH == 0) fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr, nullptr);
+  else if (MECH == 1) Hg_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr, nullptr);
+  else carbon_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, nullptr, nullptr, nullptr, nullptr);
 }
 
 __global__ void fill_int_kernel(int *p, int n, int v)
@@ -136,14 +143,14 @@ cudaError_t measure_fp64_peak(double *tflops, double *ms_out)
 cudaError_t launch_update_rconst(int mech_id, int ncell, const double *temp, const double *numden,
                                  const double *h2o, const double *photol, const double *khet,
                                  double *rconst, cudaStream_t s, int stride, int ostride,
-                                 const double *het, const double *conc, const double *srmw)
+                                 const double *het, const double *conc, const double *srmw, int nspec_data)
 {
   int blocks = (ncell + 127) / 128;
   if (stride <= 0) stride = ncell;
   if (ostride <= 0) ostride = stride;
-  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
-  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
-  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw);
+  if (mech_id == 0) update_rconst_kernel<0><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw, nspec_data);
+  else if (mech_id == 1) update_rconst_kernel<1><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw, nspec_data);
+  else update_rconst_kernel<2><<<blocks, 128, 0, s>>>(ncell, stride, ostride, temp, numden, h2o, photol, khet, rconst, het, conc, srmw, nspec_data);
   return cudaGetLastError();
 }
 __global__ void iota_kernel(int *p, int n)

@@ -69,6 +69,7 @@ def load_library(path=None):
     L.gckpp_gpu_warp_plan.argtypes = [C.c_int, ip, C.c_int, vp, C.c_int64]
     L.gckpp_gpu_set_sr_mw.argtypes = [vp, C.c_int, vp]
     L.gckpp_gpu_set_het.argtypes = [vp, vp, vp]
+    L.gckpp_gpu_set_species_data.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     for sfx in ("", "_device"):
         getattr(L, "gckpp_gpu_zero_species" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp]
         getattr(L, "gckpp_gpu_post_integrate" + sfx).argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
@@ -85,7 +86,8 @@ EXPORTS = ["gckpp_gpu_dims", "gckpp_gpu_spc_name", "gckpp_gpu_init", "gckpp_gpu_
            "gckpp_gpu_fp64_peak", "gckpp_gpu_plan_info", "gckpp_gpu_set_keep_active", "gckpp_gpu_warp_plan",
            "gckpp_gpu_zero_species", "gckpp_gpu_zero_species_device", "gckpp_gpu_post_integrate",
            "gckpp_gpu_post_integrate_device", "gckpp_gpu_prod_loss", "gckpp_gpu_prod_loss_device",
-           "gckpp_gpu_oh_reactivity", "gckpp_gpu_oh_reactivity_device", "gckpp_gpu_set_sr_mw", "gckpp_gpu_set_het"]
+           "gckpp_gpu_oh_reactivity", "gckpp_gpu_oh_reactivity_device", "gckpp_gpu_set_sr_mw", "gckpp_gpu_set_het",
+           "gckpp_gpu_set_species_data"]
 
 
 def plan_info(mech):
@@ -329,11 +331,24 @@ class KppSolver:
         return x
 
     # ------------------------------------------------------------------ heterogeneous laws on the device
-    NHET = 48
+    NHET = 96
+    # rows 0-47: first part; rows 48-95: second part (read only after set_species_data); order = include/gckpp_gpu.h
     HET_FIELDS = ("SUNCOS", "stratBox", "SSA_is_Alk", "SSA_is_Acid", "SSC_is_Alk", "SSC_is_Acid", "f_Alk_SSA", "f_Alk_SSC",
                   "f_Acid_SSA", "f_Acid_SSC", "ClearFr", "aClArea", "aClRadi", "Cl_conc_SSA", "Cl_conc_SSC", "gamma_HO2",
                   "H_PLUS", "NO3_molal", "SO4_molal", "HSO4_molal") + tuple("xArea%d" % k for k in range(1, 15)) + \
-        tuple("xRadi%d" % k for k in range(1, 15))
+        tuple("xRadi%d" % k for k in range(1, 15)) + \
+        ("natSurface", "TurnOffHetRates", "CldFr", "aIce", "aLiq", "rIce", "rLiq", "pHCloud", "pHSSA1", "pHSSA2",
+         "Cl_conc_Cld", "Br_conc_Cld", "Br_conc_SSA", "Br_conc_SSC", "Br_over_Cl_Cld", "Br_over_Cl_SSA", "Br_over_Cl_SSC",
+         "frac_Br_CldA", "frac_Br_CldC", "frac_Br_CldG", "frac_Cl_CldA", "frac_Cl_CldC", "frac_Cl_CldG", "frac_SALACL",
+         "frac_HSO3_aq", "HSO3m", "HCl_theta", "HBr_theta", "HNO3_theta", "H_conc_LCl", "H_conc_SSA", "H_conc_SSC",
+         "HSO3_aq", "SO3_aq", "TSO3_aq", "aWater1", "aWater2") + tuple("KHETI_SLA%d" % k for k in range(1, 12))
+
+    def set_species_data(self, sr_mw, mw, henry_k0, henry_cr):
+        """set_sr_mw plus MW, HENRY_K0, HENRY_CR (1:NSPEC) of gckpp_Global: switches the second part of the device-side
+        heterogeneous laws on (cloud / halogen uptake, fullchem_RateLawFuncs.F90:803-3238)"""
+        n = self.dims["nspec"]
+        a = [_np(x, np.float64, (n,), nm) for x, nm in ((sr_mw, "sr_mw"), (mw, "mw"), (henry_k0, "henry_k0"), (henry_cr, "henry_cr"))]
+        self._check(self.L.gckpp_gpu_set_species_data(self.h, n, *[_ptr(x) for x in a]), "set_species_data")
 
     def set_sr_mw(self, sr_mw):
         """SR_MW(1:NSPEC) of gckpp_Global (SQRT of the molecular weights); None switches the device-side laws off"""

@@ -136,9 +136,24 @@ enum {
   GCKPP_HET_GAMMA_HO2, GCKPP_HET_H_PLUS, GCKPP_HET_NO3_MOLAL, GCKPP_HET_SO4_MOLAL, GCKPP_HET_HSO4_MOLAL,
   GCKPP_HET_XAREA = 20,   /* xArea(1:14): DU1..DU7, SUL, BKC, ORC, SSA, SSC, SLA, IIC */
   GCKPP_HET_XRADI = 34,   /* xRadi(1:14) */
-  GCKPP_NHET = 48
+  /* second part (read only when gckpp_gpu_set_species_data was called): the cloud / halogen laws */
+  GCKPP_HET_NATSURFACE = 48, GCKPP_HET_TURNOFFHETRATES, GCKPP_HET_CLDFR, GCKPP_HET_AICE, GCKPP_HET_ALIQ, GCKPP_HET_RICE,
+  GCKPP_HET_RLIQ, GCKPP_HET_PHCLOUD, GCKPP_HET_PHSSA /* (1:2) */, GCKPP_HET_CL_CONC_CLD = 58, GCKPP_HET_BR_CONC_CLD,
+  GCKPP_HET_BR_CONC_SSA, GCKPP_HET_BR_CONC_SSC, GCKPP_HET_BR_OVER_CL_CLD, GCKPP_HET_BR_OVER_CL_SSA, GCKPP_HET_BR_OVER_CL_SSC,
+  GCKPP_HET_FRAC_BR_CLDA, GCKPP_HET_FRAC_BR_CLDC, GCKPP_HET_FRAC_BR_CLDG, GCKPP_HET_FRAC_CL_CLDA, GCKPP_HET_FRAC_CL_CLDC,
+  GCKPP_HET_FRAC_CL_CLDG, GCKPP_HET_FRAC_SALACL, GCKPP_HET_FRAC_HSO3_AQ, GCKPP_HET_HSO3M, GCKPP_HET_HCL_THETA,
+  GCKPP_HET_HBR_THETA, GCKPP_HET_HNO3_THETA, GCKPP_HET_H_CONC_LCL, GCKPP_HET_H_CONC_SSA, GCKPP_HET_H_CONC_SSC,
+  GCKPP_HET_HSO3_AQ, GCKPP_HET_SO3_AQ, GCKPP_HET_TSO3_AQ, GCKPP_HET_AWATER /* (1:2) */, GCKPP_HET_KHETI_SLA = 85 /* (1:11) */,
+  GCKPP_NHET = 96
 };
 int gckpp_gpu_set_sr_mw(gckpp_gpu_handle_t *handle, int n, const double *sr_mw);
+/* set_sr_mw plus MW(1:NSPEC) [g/mol] and the Henry's-law constants HENRY_K0 [M/atm], HENRY_CR [K] of gckpp_Global: enables
+ * the second part -- 35 more constants (BrNO3, ClNO2, ClNO3, HOBr, HOCl, IONO2, O3 + bromide, NO2 / NO3 uptake and cloud
+ * loss, NO3 on sea-salt chloride, N2O5 in cloud / + stratospheric HCl; fullchem_RateLawFuncs.F90:803-3238).  17 constants
+ * then remain external: K_MT(6), K_CLD(6), the three N2O5 laws that use N2O5_InorgOrg and the two HSO3m / SO3mm sums
+ * that add the sulfur module's SRHOCl / SRHOBr. */
+int gckpp_gpu_set_species_data(gckpp_gpu_handle_t *handle, int n, const double *sr_mw, const double *mw,
+                               const double *henry_k0, const double *henry_cr);
 int gckpp_gpu_set_het(gckpp_gpu_handle_t *handle, const double *het, const double *conc);
 
 /* Fun(V,F,RCT,Vdot,Aout) over cells (RxnRate diagnostics, fullchem_mod.F90:967-992):

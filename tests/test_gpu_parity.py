@@ -549,3 +549,108 @@ def test_heterogeneous_laws_on_device_vs_oracle(solver, oracle):
         solver.set_option("wave_cells", 0)
         solver.set_het(None)
         solver.set_sr_mw(None)
+
+
+@pytest.mark.gpu
+def test_heterogeneous_laws_second_part_vs_oracle(solver, oracle):
+    """SURVEY 8 f1, second part: with the species data (SR_MW, MW, HENRY_K0, HENRY_CR) and the 96 HetState fields,
+    Update_RCONST also evaluates the cloud / halogen uptake laws (35 more constants: BrNO3, ClNO2, ClNO3, HOBr, HOCl,
+    IONO2, N2O5 in cloud / + stratospheric HCl, NO2 / NO3 uptake, NO3 on sea-salt chloride, O3 + bromide;
+    fullchem_RateLawFuncs.F90:803-3238).  GPU against the scalar Python restatement of the Fortran
+    (oracle/het_oracle.py), 1e-10 relative (libm differences pass through the reacto-diffusive and entrainment
+    expressions, which cancel).  Parity unpinned by the reference."""
+    from oracle import het_oracle as ho
+    from geos_chem_b200.kppgen import ir
+    m = ir.load("fullchem")
+    n = 512
+    g = grid.make_grid("4x5", limit=30000)
+    rng = np.random.default_rng(43)
+    idx = np.sort(rng.choice(30000, n, replace=False))
+    sub = lambda a: np.ascontiguousarray(a[..., idx])
+    temp, numden, h2o, photol, khet, conc = map(sub, (g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"], g["conc"]))
+    F = kpp.KppSolver.HET_FIELDS
+    assert len(F) == kpp.KppSolver.NHET == 96
+    het = np.zeros((kpp.KppSolver.NHET, n))
+    col = {name: k for k, name in enumerate(F)}
+    logu = lambda lo, hi: 10 ** rng.uniform(lo, hi, n)
+    some0 = lambda a, p=0.1: np.where(rng.uniform(size=n) < p, 0.0, a)
+    het[col["SUNCOS"]] = rng.uniform(-0.5, 1.0, n)
+    for flag in ("stratBox", "SSA_is_Alk", "SSA_is_Acid", "SSC_is_Alk", "SSC_is_Acid", "natSurface"):
+        het[col[flag]] = (rng.uniform(size=n) < 0.4).astype(np.float64)
+    het[col["TurnOffHetRates"]] = (rng.uniform(size=n) < 0.1).astype(np.float64)
+    for fr in ("f_Alk_SSA", "f_Alk_SSC", "f_Acid_SSA", "f_Acid_SSC", "frac_Br_CldA", "frac_Br_CldC", "frac_Br_CldG",
+               "frac_Cl_CldA", "frac_Cl_CldC", "frac_Cl_CldG", "frac_SALACL", "frac_HSO3_aq", "HSO3m", "HCl_theta",
+               "HBr_theta", "HNO3_theta"):
+        het[col[fr]] = rng.uniform(0.0, 1.0, n)
+    het[col["ClearFr"]] = np.where(rng.uniform(size=n) < 0.05, 0.0, rng.uniform(0.0, 1.0, n))       # overcast boxes too
+    het[col["CldFr"]] = np.where(rng.uniform(size=n) < 0.15, 5e-5, 1.0 - het[col["ClearFr"]])
+    het[col["aLiq"]] = some0(logu(-8, -4), 0.2); het[col["aIce"]] = some0(logu(-8, -4), 0.3)
+    het[col["rLiq"]] = logu(-3.3, -2.7); het[col["rIce"]] = logu(-2.7, -2.0)
+    het[col["pHCloud"]] = rng.uniform(1.0, 7.0, n)
+    het[col["pHSSA1"]] = rng.uniform(0.0, 8.0, n); het[col["pHSSA2"]] = rng.uniform(0.0, 8.0, n)
+    het[col["aClArea"]] = logu(-9, -6); het[col["aClRadi"]] = logu(-6, -4)
+    for f in ("Cl_conc_SSA", "Cl_conc_SSC"):
+        het[col[f]] = some0(logu(-2, 1))
+    het[col["Cl_conc_Cld"]] = some0(logu(-7, -2))
+    for f in ("Br_conc_Cld", "Br_conc_SSA", "Br_conc_SSC"):
+        het[col[f]] = some0(logu(-10, -3), 0.15)
+    for f in ("Br_over_Cl_Cld", "Br_over_Cl_SSA", "Br_over_Cl_SSC"):
+        het[col[f]] = some0(logu(-6, -2))                    # both sides of 5e-4 and of the Br2 yield's clamps
+    for f in ("H_conc_LCl", "H_conc_SSA", "H_conc_SSC"):
+        het[col[f]] = logu(-10, -1)
+    for f in ("HSO3_aq", "SO3_aq", "TSO3_aq"):
+        het[col[f]] = some0(logu(-10, -4), 0.2)
+    het[col["aWater1"]] = logu(9, 13); het[col["aWater2"]] = logu(9, 13)
+    for k in range(1, 12):
+        het[col["KHETI_SLA%d" % k]] = some0(logu(-8, -2), 0.3)
+    het[col["gamma_HO2"]] = rng.uniform(0.0, 0.3, n)
+    het[col["H_PLUS"]] = logu(-6, -2)
+    for mol in ("NO3_molal", "SO4_molal", "HSO4_molal"):
+        het[col[mol]] = logu(-3, 1)
+    for k in range(1, 15):
+        het[col["xArea%d" % k]] = some0(logu(-10, -6), 0.15)
+        het[col["xRadi%d" % k]] = logu(-6.5, -3.5)
+    h2o = h2o * 10 ** rng.uniform(-0.5, 1.0, n)
+    mw = rng.uniform(17.0, 300.0, m.nspec)
+    sr_mw = np.sqrt(mw)
+    hk0 = 10 ** rng.uniform(-2, 4, m.nspec)
+    hcr = rng.uniform(0.0, 8000.0, m.nspec)
+    cells = [ho.Cell(temp[c], numden[c], h2o[c], het[:, c], sr_mw, conc[:, c], F) for c in range(n)]
+    want1 = [ho.evaluate(m.rconst, m.ind, cl) for cl in cells]
+    want2 = [ho.evaluate2(m.rconst, m.ind, cl, mw, hk0, hcr) for cl in cells]
+    rows1, rows2 = sorted(want1[0]), sorted(want2[0])
+    assert len(rows1) == 61 and len(rows2) == 35 and not set(rows1) & set(rows2)
+    ref = oracle.update_rconst("fullchem", temp, numden, h2o, photol, khet)
+    exp = ref.copy()
+    for c in range(n):
+        for r in rows1:
+            exp[r, c] = want1[c][r]
+        for r in rows2:
+            exp[r, c] = want2[c][r]
+    pos = (exp[rows2] > 0).mean(axis=1)
+    assert (pos > 0.02).all(), [(rows2[i], m.rconst[rows2[i]]) for i in np.nonzero(pos <= 0.02)[0]]   # every law is exercised
+    solver.set_species_data(sr_mw, mw, hk0, hcr)
+    try:
+        solver.set_het(het, conc)
+        rc = solver.Update_RCONST(temp, numden, h2o, photol, khet)
+        rows = rows1 + rows2
+        # a zero aerosol area makes Gam_NO3 divide by a zero volume: NaN in the reference's arithmetic, NaN here
+        nan = np.isnan(exp[rows])
+        assert np.array_equal(nan, np.isnan(rc[rows])) and nan.mean() < 0.01
+        err = np.where(nan, 0.0, np.abs(rc[rows] - exp[rows]) / np.maximum(np.abs(exp[rows]), 1e-300))
+        worst = np.unravel_index(np.argmax(err), err.shape)
+        print("device het laws, both parts: max rel err %.2e over %d constants x %d cells (worst: %s)"
+              % (err.max(), len(rows), n, m.rconst[rows[worst[0]]]))
+        assert err.max() <= 1e-10
+        others = np.setdiff1d(np.arange(m.nreact), rows)
+        solver.set_het(None)
+        rc0 = solver.Update_RCONST(temp, numden, h2o, photol, khet)
+        assert np.array_equal(rc[others], rc0[others]) and np.array_equal(rc0[rows], ref[rows])
+        # SR_MW alone: the second part stays with khet
+        solver.set_sr_mw(sr_mw)
+        solver.set_het(het, conc)
+        rc1 = solver.Update_RCONST(temp, numden, h2o, photol, khet)
+        assert np.array_equal(rc1[rows2], ref[rows2]) and np.array_equal(rc1[rows1], rc[rows1], equal_nan=True)
+    finally:
+        solver.set_het(None)
+        solver.set_sr_mw(None)
