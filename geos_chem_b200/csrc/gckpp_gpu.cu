@@ -124,7 +124,7 @@ struct gckpp_gpu_handle {
   int sm_ready = 0, sm_blocks_cap = 0;
   SmemHostPlan plan;
   SmemArgs sargs{};
-  DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag;
+  DevBuf sm_rcs, sm_scr, sm_stream, sm_res, sm_boff, sm_dir, sm_tpos, sm_crow, sm_aw, sm_bw, sm_coefs, sm_diag, sm_rowcol, ar_mask;
   int last_kernel = 0;
   DevBuf sm_uscale;
   // warp-per-cell kernel: host plan + device copies of its tables
@@ -265,7 +265,7 @@ extern "C" int gckpp_gpu_finalize(gckpp_gpu_handle_t *h)
                     &h->w_stream, &h->w_aw, &h->w_bw, &h->w_diag, &h->w_tpos, &h->w_coefs, &h->w_rcs,
                     &h->l_tab[0], &h->l_tab[1], &h->l_tab[2], &h->l_tab[3], &h->l_tab[4], &h->l_tab[5], &h->l_tab[6], &h->l_lit, &h->l_ws,
                     &h->small, &h->srmw,
-                    &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag};
+                    &h->keep_spc, &h->sm_uscale, &h->ident, &h->sm_rcs, &h->sm_scr, &h->sm_stream, &h->sm_res, &h->sm_boff, &h->sm_dir, &h->sm_tpos, &h->sm_crow, &h->sm_aw, &h->sm_bw, &h->sm_coefs, &h->sm_diag, &h->sm_rowcol, &h->ar_mask};
   for (DevBuf *b : bufs) b->release();
   free_slots(h);
   for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -477,6 +477,7 @@ static int prepare_smem(gckpp_gpu_handle *h)
     {&h->sm_tpos, S->tpos, 32 * 32 * 2},                   {&h->sm_diag, p.diag.data(), p.diag.size() * 2},
     {&h->sm_crow, p.crow.data(), p.crow.size() * 2},       {&h->sm_aw, p.aw.data(), p.aw.size() * 4},
     {&h->sm_bw, p.bw.data(), p.bw.size() * 4},             {&h->sm_uscale, p.uscale.data(), p.uscale.size() * 4},             {&h->sm_coefs, S->coefs, sizeof(double) * (size_t)S->ncoef},
+    {&h->sm_rowcol, p.rowcol.data(), p.rowcol.size() * 4},
   };
   for (Up &u : ups) {
     if (u.b->ensure(u.bytes ? u.bytes : 16)) return fail(-1002, "out of device memory for the kernel tables");
@@ -594,9 +595,17 @@ static int prepare_lane(gckpp_gpu_handle *h)
   return 0;
 }
 
+static int choose_kernel_plain(gckpp_gpu_handle *h, const Decoded &d);
 static int choose_kernel(gckpp_gpu_handle *h, const Decoded &d)
 {
-  if (d.autoreduce) return 0;                // auto-reduce runs on the table-driven kernel
+  const int k = choose_kernel_plain(h, d);
+  // auto-reduce: the block kernel integrates on the full pattern with a per-cell keep mask (its AR instance); every
+  // other choice falls back to the table-driven kernel, which carries the reference-order implementation
+  if (d.autoreduce && k != 1) return 0;
+  return k;
+}
+static int choose_kernel_plain(gckpp_gpu_handle *h, const Decoded &d)
+{
   if (h->opt_kernel == 0) return 0;          // "kernel"=0 forces the table-driven, reference-order kernel
   if (h->T->nnz <= 0) return 0;
   if (h->opt_kernel == 3) return host_lsched(h->mech_id) ? 3 : 0;     // lane kernel: every method
@@ -664,7 +673,16 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
     int nb = (nwork + SMEM_NC - 1) / SMEM_NC;
     if (nb > h->sm_count) nb = h->sm_count;
     if (h->sm_blocks_cap > 0 && nb > h->sm_blocks_cap) nb = h->sm_blocks_cap;
-    CUDA_TRY(launch_ros_smem(h->mech_id, h->sargs, a, nb, h->stream));
+    if (d.autoreduce) {
+      // the decision pass (Prod / LossY against the threshold at the initial state), then the AR instance; its two
+      // extra pointers travel in RosArgs fields the block kernel does not read (see ros_smem.cu)
+      if (h->ar_mask.ensure((size_t)h->T->nvar * (size_t)ncell)) return fail(-1002, "out of device memory for the auto-reduce masks");
+      CUDA_TRY(launch_ar_mask(h->M, a, h->ar_mask.as<unsigned char>(), h->stream));
+      a.work = reinterpret_cast<double *>(h->ar_mask.p);
+      a.ar_keep_spc = reinterpret_cast<const unsigned char *>(h->sm_rowcol.p);
+      h->stats[6] += 1;
+    }
+    CUDA_TRY(launch_ros_smem(h->mech_id, h->sargs, a, nb, h->stream, d.autoreduce != 0));
     h->last_kernel = 1;
   } else {
     h->last_kernel = 0;

@@ -441,6 +441,56 @@ cudaError_t launch_feuler(const MechDev &M, const RosArgs &a, int icntrl16, cuda
   feuler_kernel<<<(a.nwork + 127) / 128, 128, 0, s>>>(M, a, icntrl16);
   return cudaGetLastError();
 }
+// Auto-reduce decision of ros_yIntegrator (gckpp_Integrator.F90:904-962) as a pass of its own, for the kernels that
+// integrate on the full pattern with a per-cell keep mask: one cell per thread, Prod = P_VAR and LossY = D_VAR * V from
+// FunSplitF at (Tstart, the initial concentrations), in the reference's summation order (this unit has no FMA
+// contraction); a rate A(r) is re-evaluated where the reference reads it from the array -- same operations, same bits.
+// mask[i][cell] = 0 when species i leaves the implicit system.  rstatus(NARthr) receives the threshold used.
+__device__ __forceinline__ double term_eval2(int4 t, const double *yv, size_t sy, const double *rc, size_t sr, const double *__restrict__ lit)
+{
+  double x = t.x >= 0 ? rc[(size_t)t.x * sr] : __ldg(lit + (~t.x));
+  if (t.y != -1) x = x * (t.y >= 0 ? yv[(size_t)t.y * sy] : __ldg(lit + (-2 - t.y)));
+  if (t.z != -1) x = x * (t.z >= 0 ? yv[(size_t)t.z * sy] : __ldg(lit + (-2 - t.z)));
+  if (t.w != -1) x = x * (t.w >= 0 ? yv[(size_t)t.w * sy] : __ldg(lit + (-2 - t.w)));
+  return x;
+}
+__device__ __forceinline__ void prod_loss(const MechDev &M, int i, const double *yv, size_t sy, const double *rc, size_t sr, double &P, double &D)
+{
+  P = 0.0; D = 0.0;
+  int e = __ldg(M.p_ptr + i + 1);
+  for (int k = __ldg(M.p_ptr + i); k < e; k++)
+    P = P + __ldg(M.p_coef + k) * term_eval2(__ldg(M.a_term + __ldg(M.p_rxn + k)), yv, sy, rc, sr, M.lit);
+  e = __ldg(M.d_ptr + i + 1);
+  for (int k = __ldg(M.d_ptr + i); k < e; k++) D = D + term_eval2(__ldg(M.d_term + k), yv, sy, rc, sr, M.lit);
+}
+__global__ void __launch_bounds__(128) ar_mask_kernel(MechDev M, RosArgs a, unsigned char *__restrict__ mask)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.nwork) return;
+  const int cell = a.cell_list ? a.cell_list[w] : w;
+  const double *yv = a.conc_in + cell, *rc = a.rconst + (cell - a.rc_cell0);
+  const size_t sy = (size_t)a.ncell, sr = (size_t)a.rc_stride;
+  double thr = a.ar_threshold, arthr = 0.0, P, D;
+  if (a.ar_target > 0) {
+    const int t = a.ar_target - 1;
+    prod_loss(M, t, yv, sy, rc, sr, P, D);
+    thr = a.ar_ratio * fmax(D * yv[(size_t)t * sy], P);
+    arthr = thr;
+  }
+  for (int i = 0; i < M.nvar; i++) {
+    prod_loss(M, i, yv, sy, rc, sr, P, D);
+    const bool keep = a.ar_keep_active && a.ar_keep_spc && a.ar_keep_spc[i];
+    const bool rmv = !keep && fabs(D * yv[(size_t)i * sy]) < thr && fabs(P) < thr;
+    mask[(size_t)i * sy + cell] = rmv ? 0 : 1;
+  }
+  if (a.rstatus) a.rstatus[(size_t)3 * a.ncell + cell] = arthr;
+}
+cudaError_t launch_ar_mask(const MechDev &M, const RosArgs &a, unsigned char *mask, cudaStream_t s)
+{
+  if (!M.fun_split) return cudaErrorInvalidValue;
+  ar_mask_kernel<<<(a.nwork + 127) / 128, 128, 0, s>>>(M, a, mask);
+  return cudaGetLastError();
+}
 cudaError_t launch_ros_generic(const MechDev &M, const RosArgs &a, int blocks, int threads, cudaStream_t s)
 {
   ros_generic_kernel<<<blocks, threads, 0, s>>>(M, a);

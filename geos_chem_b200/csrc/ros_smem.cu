@@ -334,7 +334,14 @@ __device__ __forceinline__ void tail_bwd(const double *Gc, double *Xc, const uin
   if (lane < m) Xc[M::HEAD + lane] = x;
 }
 
-template <class M>
+// AR = auto-reduce on the full pattern (ros_yIntegrator, gckpp_Integrator.F90:789-1237): the keep mask of every cell
+// comes from ar_mask_kernel; rows and columns of removed species are turned into identity rows / zero columns after
+// the Jacobian round and their right-hand sides are zero, so the kept rows see exactly the operations of the reference's
+// compressed system (cKppDecomp / cKppSolve, :2624-2720) and K of a removed species is 0.  The non-AR instance is the
+// unchanged production kernel; to keep its parameter block (and with it its register allocation) as it was, the AR
+// instance receives its two extra pointers in fields of RosArgs this kernel does not otherwise read:
+//   a.work = keep mask [NVAR][ncell] (bytes), a.ar_keep_spc = (row | col << 16) of every matrix entry (uint32).
+template <class M, bool AR>
 __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 {
   using L = Lay<M>;
@@ -358,6 +365,10 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   uint32_t *dir = reinterpret_cast<uint32_t *>(smem + P.s_dir);
   uint16_t *diag = reinterpret_cast<uint16_t *>(smem + P.s_diag);
   uint16_t *crow = reinterpret_cast<uint16_t *>(smem + P.s_crow);
+  unsigned char *MK = smem + P.s_crow + (((M::NVAR + 1) * 2 + 15) & ~15);      // [NC][NVAR] keep flags (AR only)
+  const unsigned char *ar_mask = reinterpret_cast<const unsigned char *>(a.work);
+  const uint32_t *ar_rowcol = reinterpret_cast<const uint32_t *>(a.ar_keep_spc);
+  unsigned mk = 0xffffffffu;                                                 // bit c: species tid of slot c is kept
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const RosOpts &o = a.o;
@@ -474,11 +485,16 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         if (tid < M::NSPEC) a.conc_out[(size_t)tid * a.ncell + oc] = Y[c];
         if (tid < 8 && a.istatus) a.istatus[(size_t)tid * a.ncell + oc] = slot[c].out_ist[tid];
         if (tid >= 32 && tid < 35 && a.rstatus) a.rstatus[(size_t)(tid - 32) * a.ncell + oc] = slot[c].out_r[tid - 32];
-        if (tid == 35 && a.rstatus) a.rstatus[(size_t)3 * a.ncell + oc] = 0.0;
+        if (!AR && tid == 35 && a.rstatus) a.rstatus[(size_t)3 * a.ncell + oc] = 0.0;     // AR: NARthr was stored by ar_mask_kernel
         if (tid == 36 && a.ierr) a.ierr[oc] = slot[c].out_ierr;
       }
       if (ic >= 0) {
         if (tid < M::NSPEC) Y[c] = a.conc_in[(size_t)tid * a.ncell + ic];
+        if (AR && tid < N) {
+          const unsigned char v = ar_mask[(size_t)tid * a.ncell + ic];
+          MK[c * N + tid] = v;
+          mk = (mk & ~(1u << c)) | (v ? (1u << c) : 0u);
+        }
 #pragma unroll
         for (int k = 0; k < NA_IT; k++) {
           const int r = k * NT + tid;
@@ -579,6 +595,18 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         __syncthreads();
         stream_round(std::integral_constant<int, OP_JVS>(), dir[1]);
         __syncthreads();
+        if (AR) {
+          for (int k = tid; k < M::NNZ; k += NT) {
+            const uint32_t rcw = __ldg(ar_rowcol + k);
+            const int row = rcw & 0xffff, col = rcw >> 16;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+              const bool kr = MK[c * N + row] != 0, kc = MK[c * N + col] != 0;
+              if (!kr || !kc) G[c * L::GS + k] = (!kr && row == col) ? 1.0 : 0.0;
+            }
+          }
+          __syncthreads();
+        }
         PROF(2);
         // ---- sparse LU  (KppDecomp): head pivots by DAG level, then the tail block
 #pragma unroll 1
@@ -606,7 +634,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         // columns, which are final, and never touch the tail block.
         if (tid < N) {
 #pragma unroll
-          for (int c = 0; c < NC; c++) X[c * N + tid] = F0[c];
+          for (int c = 0; c < NC; c++) X[c * N + tid] = (AR && !((mk >> c) & 1u)) ? 0.0 : F0[c];
         }
         __syncthreads();
         if (warp < NC) {
@@ -662,6 +690,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
             else if (st == 1) v = fma(o.C[0] / dh[c], K1[c], F0[c]);
             else if (st == 2) v = fma(o.C[2] / dh[c], K2[c], fma(o.C[1] / dh[c], K1[c], X[c * N + tid]));
             else v = fma(o.C[5] / dh[c], K3[c], fma(o.C[4] / dh[c], K2[c], fma(o.C[3] / dh[c], K1[c], X[c * N + tid])));
+            if (AR && !((mk >> c) & 1u)) v = 0.0;
             X[c * N + tid] = v;
           }
         }
@@ -979,14 +1008,18 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   hp.s_dir = take(hp.dir.size() * 4);
   hp.s_diag = take(hp.diag.size() * 2);
   hp.s_crow = take(hp.crow.size() * 2);
+  take((size_t)NC * T->nvar);                  // keep flags of the auto-reduce instance, right behind crow
   hp.s_total = off;
+  hp.rowcol.resize(T->nnz);
+  for (int i = 0; i < T->nvar; i++)
+    for (int k = T->crow[i]; k < T->crow[i + 1]; k++) hp.rowcol[k] = (uint32_t)i | ((uint32_t)T->icol[k] << 16);
   return 0;
 }
 
-template <class M>
+template <class M, bool AR>
 static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s)
 {
-  auto k = ros_smem_kernel<M>;
+  auto k = ros_smem_kernel<M, AR>;
   // the opt-in is a per-DEVICE attribute of the function (one process may hold handles on several GPUs): set it on
   // every launch -- it is cheap -- rather than cache it per process
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.s_total);
@@ -995,9 +1028,11 @@ static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, cud
   return cudaGetLastError();
 }
 
-cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s)
+cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s, bool autoreduce)
 {
-  if (mech_id == GCKPP_MECH_FULLCHEM) return launch_t<fullchem_dims>(P, a, blocks, s);
-  if (mech_id == GCKPP_MECH_HG) return launch_t<Hg_dims>(P, a, blocks, s);
+  if (mech_id == GCKPP_MECH_FULLCHEM && autoreduce) return launch_t<fullchem_dims, true>(P, a, blocks, s);
+  if (autoreduce) return cudaErrorInvalidConfiguration;
+  if (mech_id == GCKPP_MECH_FULLCHEM) return launch_t<fullchem_dims, false>(P, a, blocks, s);
+  if (mech_id == GCKPP_MECH_HG) return launch_t<Hg_dims, false>(P, a, blocks, s);
   return cudaErrorInvalidConfiguration;
 }

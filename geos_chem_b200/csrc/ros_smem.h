@@ -71,7 +71,7 @@ struct SmemArgs {
 
 struct SmemHostPlan {
   int warp_off[SMEM_NW], warp_rows[SMEM_NW];
-  std::vector<uint32_t> stream, resident, dir, aw, bw, uscale;
+  std::vector<uint32_t> stream, resident, dir, aw, bw, uscale, rowcol;
   std::vector<uint16_t> boff, diag, crow;
   int o_lu, n_lu, o_fwd, n_fwd, o_bwd, n_bwd, o_fwd1;
   int s_res, s_tpos, s_boff, s_dir, s_diag, s_crow, s_total;
@@ -81,4 +81,4 @@ bool smem_kernel_supports(int mech_id);
 int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched_tables_t *S, SmemHostPlan &hp);
 size_t smem_rcs_doubles_per_block(int mech_id);
 size_t smem_scr_doubles_per_block(int mech_id);
-cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s);
+cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s, bool autoreduce = false);

@@ -199,11 +199,14 @@ def test_standalone_box_model_cli(tmp_path, fx, capsys):
         assert lines[0].startswith("Species Name,") and len(lines) == 1 + 356
 
 
+@pytest.mark.parametrize("kernel", ["block", "table"])
 @pytest.mark.parametrize("mode", ["target_OH", "fixed_threshold"])
-def test_autoreduce_vs_oracle(solver, oracle, fx, mode):
+def test_autoreduce_vs_oracle(solver, oracle, fx, mode, kernel):
     """config 5: fullchem with the auto-reduce solver (ros_yIntegrator, gckpp_Integrator.F90:789-1237), options as
-    fullchem_AutoReduceFuncs.F90:275-342 sets them.  Parity is unpinned by the reference (no fixture): the GPU
-    (table-driven kernel, mask form of the compressed system) is compared with the oracle's restatement."""
+    fullchem_AutoReduceFuncs.F90:275-342 sets them.  Parity is unpinned by the reference (no fixture): the GPU (mask
+    form of the compressed system; the block kernel's AR instance behind a decision pass = the default, and the
+    table-driven reference-order kernel) is compared with the oracle's restatement."""
+    solver.set_option("kernel", -1 if kernel == "block" else 0)
     names = fx["names"]
     keep = grid.keep_active_indices(names[:353])
     g = grid.make_grid("4x5", limit=40000)
@@ -224,15 +227,17 @@ def test_autoreduce_vs_oracle(solver, oracle, fx, mode):
     try:
         co, isto, rsto, ierro = oracle.integrate("fullchem", 0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, rcntrl, hstart=hs)
         c, ist, rst, ierr, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], icntrl, rcntrl, hstart=hs)
+        assert solver.last_stats()["kernel"] == (1 if kernel == "block" else 0)
         # and the unreduced solution, to show that the option does something
         cf, _, _, _, _ = solver.Integrate(0.0, 1200.0, conc, rc, g["atol"], g["rtol"], g["icntrl"], g["rcntrl"], hstart=hs)
     finally:
         oracle.set_keep_active("fullchem", [])
         solver.set_keep_active([])
+        solver.set_option("kernel", -1)
     assert np.array_equal(ierr, ierro)
     same = np.all(ist == isto, axis=0)
     rel = _parity(c, co)
-    print("auto-reduce %s: cells with different steps %d, max rel err %.3e; species changed vs full solve: %.1f %%; "
+    print("auto-reduce %s (" + kernel + " kernel): cells with different steps %d, max rel err %.3e; species changed vs full solve: %.1f %%; "
           "ARthr max rel diff %.2e" % (mode, int((~same).sum()), rel.max(), 100.0 * np.mean(c[:353] != cf[:353]),
                                        np.abs(rst[3] - rsto[3]).max() / max(np.abs(rsto[3]).max(), 1e-300)))
     assert rel.max() <= 1e-4
