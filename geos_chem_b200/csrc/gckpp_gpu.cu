@@ -628,7 +628,9 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
                           int rc_stride = 0, int rc_cell0 = 0)
 {
   if (nwork <= 0) return 0;
-  const int kern = choose_kernel(h, d);
+  int kern = choose_kernel(h, d);
+  // the block kernel's auto-reduce instance closes with a pass that reads conc_in and ierr: without them, kernel 0
+  if (d.autoreduce && kern == 1 && (!ierr || conc_in == conc_out)) kern = 0;
   const bool smem = kern == 1;
   int blocks = (nwork + h->threads - 1) / h->threads;
   if (blocks > h->max_blocks) blocks = h->max_blocks;
@@ -683,6 +685,10 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
       h->stats[6] += 1;
     }
     CUDA_TRY(launch_ros_smem(h->mech_id, h->sargs, a, nb, h->stream, d.autoreduce != 0));
+    if (d.autoreduce) {
+      CUDA_TRY(launch_ar_first_order(h->M, a, h->ar_mask.as<unsigned char>(), h->stream));
+      h->stats[6] += 1;
+    }
     h->last_kernel = 1;
   } else {
     h->last_kernel = 0;

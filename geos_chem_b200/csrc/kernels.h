@@ -7,6 +7,7 @@
 // ros_generic.cu (compiled with -fmad=false)
 cudaError_t launch_ros_generic(const MechDev &M, const RosArgs &a, int blocks, int threads, cudaStream_t s);
 cudaError_t launch_ar_mask(const MechDev &M, const RosArgs &a, unsigned char *mask, cudaStream_t s);
+cudaError_t launch_ar_first_order(const MechDev &M, const RosArgs &a, const unsigned char *mask, cudaStream_t s);
 cudaError_t launch_feuler(const MechDev &M, const RosArgs &a, int icntrl16, cudaStream_t s);
 cudaError_t launch_fun_cells(const MechDev &M, int ncell, const double *conc, const double *rconst,
                              double *vdot, double *aout, cudaStream_t s);

@@ -485,6 +485,35 @@ __global__ void __launch_bounds__(128) ar_mask_kernel(MechDev M, RosArgs a, unsi
   }
   if (a.rstatus) a.rstatus[(size_t)3 * a.ncell + cell] = arthr;
 }
+// The closing step of the auto-reduce solver for those kernels: the removed species of every cell that finished with
+// IERR = 1 get their first-order solution (AutoReduce_1stOrder, gckpp_Integrator.F90:1702-1712, called at :1232-1236)
+// from Prod / Loss at the initial state -- re-evaluated here from conc_in exactly as ar_mask_kernel evaluated them
+// (conc_in must not alias conc_out).
+__global__ void __launch_bounds__(128) ar_first_order_kernel(MechDev M, RosArgs a, const unsigned char *__restrict__ mask)
+{
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.nwork) return;
+  const int cell = a.cell_list ? a.cell_list[w] : w;
+  if (a.ierr[cell] != 1) return;
+  const double *yv = a.conc_in + cell, *rc = a.rconst + (cell - a.rc_cell0);
+  const size_t sy = (size_t)a.ncell, sr = (size_t)a.rc_stride;
+  for (int i = 0; i < M.nvar; i++) {
+    if (mask[(size_t)i * sy + cell]) continue;
+    double P, k;
+    prod_loss(M, i, yv, sy, rc, sr, P, k);
+    const double y = a.conc_out[(size_t)i * sy + cell];
+    if (k > 1.e-30 && y > 1.e-30) {
+      const double term = P / k;
+      a.conc_out[(size_t)i * sy + cell] = term + (y - term) * exp(-k * (a.o.Tend - a.o.Tstart));
+    }
+  }
+}
+cudaError_t launch_ar_first_order(const MechDev &M, const RosArgs &a, const unsigned char *mask, cudaStream_t s)
+{
+  if (!M.fun_split || !a.ierr || a.conc_in == a.conc_out) return cudaErrorInvalidValue;
+  ar_first_order_kernel<<<(a.nwork + 127) / 128, 128, 0, s>>>(M, a, mask);
+  return cudaGetLastError();
+}
 cudaError_t launch_ar_mask(const MechDev &M, const RosArgs &a, unsigned char *mask, cudaStream_t s)
 {
   if (!M.fun_split) return cudaErrorInvalidValue;

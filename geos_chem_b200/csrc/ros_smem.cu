@@ -239,6 +239,41 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
 // broadcast with shuffles.  The row registers ROTATE by one column per pivot (r[0] is always the pivot
 // column), so the pivot loop stays rolled and the code small enough for the instruction cache.
 // Entries outside the LU pattern are exact zeros and stay zero (fill-in closure).
+// Pivots j0..j1-1 with KMAX live column slots: at pivot j only the slots 0..m-1-j can be non-zero, so the later
+// spans of the pivot loop update (and shuffle) fewer columns -- 608 column updates instead of 992 for m = 32.
+template <class M, int KMAX>
+__device__ __forceinline__ void tail_lu_span(double (&r)[M::TAIL], double &rinv, double &myrd, bool &sing, double *Gc,
+                                             const uint16_t *tposT, int lane, int j0, int j1)
+{
+#pragma unroll 1
+  for (int j = j0; j < j1; j++) {
+    const double l = (lane > j) ? r[0] * rinv : 0.0;
+    if (lane == j) {
+      myrd = rinv;
+      sing = !(fabs(r[0]) >= DBL_MIN);          // singular test of ros_PrepareMatrix, also catches NaN
+    }
+    const unsigned p = tposT[j * 32 + lane];
+    if (p != TNONE) Gc[p] = (lane > j) ? l : (lane == j ? rinv : r[0] * myrd);
+    // update column j+k and rotate it to slot k-1; shuffles issued in batches so their latency overlaps
+#pragma unroll
+    for (int k0 = 1; k0 < KMAX; k0 += 8) {
+      int hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (k0 + q < KMAX) {
+          hi[q] = __shfl_sync(FULLMASK, __double2hiint(r[k0 + q]), j);
+          lo[q] = __shfl_sync(FULLMASK, __double2loint(r[k0 + q]), j);
+        }
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (k0 + q < KMAX) r[k0 + q - 1] = fma(-l, __hiloint2double(hi[q], lo[q]), r[k0 + q]);
+      if (k0 == 1) rinv = 1.0 / __shfl_sync(FULLMASK, r[0], (j + 1) & 31);
+    }
+    if (KMAX == 1) rinv = 1.0 / __shfl_sync(FULLMASK, r[0], (j + 1) & 31);
+    r[KMAX - 1] = 0.0;
+  }
+}
+
 template <class M>
 __device__ __forceinline__ bool tail_lu(double *Gc, const uint16_t *tposT, int lane)
 {
@@ -256,32 +291,16 @@ __device__ __forceinline__ bool tail_lu(double *Gc, const uint16_t *tposT, int l
   double rinv = 1.0 / __shfl_sync(FULLMASK, r[0], 0);
   double myrd = 0.0;
   bool sing = false;
-#pragma unroll 1
-  for (int j = 0; j < m; j++) {
-    const double l = (lane > j) ? r[0] * rinv : 0.0;
-    if (lane == j) {
-      myrd = rinv;
-      sing = !(fabs(r[0]) >= DBL_MIN);          // singular test of ros_PrepareMatrix, also catches NaN
-    }
-    const unsigned p = tposT[j * 32 + lane];
-    if (p != TNONE) Gc[p] = (lane > j) ? l : (lane == j ? rinv : r[0] * myrd);
-    // update column j+k and rotate it to slot k-1; shuffles issued in batches so their latency overlaps
-#pragma unroll
-    for (int k0 = 1; k0 < m; k0 += 8) {
-      int hi[8], lo[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (k0 + q < m) {
-          hi[q] = __shfl_sync(FULLMASK, __double2hiint(r[k0 + q]), j);
-          lo[q] = __shfl_sync(FULLMASK, __double2loint(r[k0 + q]), j);
-        }
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        if (k0 + q < m) r[k0 + q - 1] = fma(-l, __hiloint2double(hi[q], lo[q]), r[k0 + q]);
-      if (k0 == 1) rinv = 1.0 / __shfl_sync(FULLMASK, r[0], (j + 1) & 31);
-    }
-    r[m - 1] = 0.0;
-  }
+#if SMEM_TAIL_SPANS
+  constexpr int Q = (m + 3) / 4;                 // four spans of the pivot loop with 4Q, 3Q, 2Q, Q (clipped to m) live slots
+  constexpr int K0 = m, K1 = m - Q > 1 ? m - Q : 1, K2 = m - 2 * Q > 1 ? m - 2 * Q : 1, K3 = m - 3 * Q > 1 ? m - 3 * Q : 1;
+  tail_lu_span<M, K0>(r, rinv, myrd, sing, Gc, tposT, lane, 0, Q < m ? Q : m);
+  if (Q < m) tail_lu_span<M, K1>(r, rinv, myrd, sing, Gc, tposT, lane, Q, 2 * Q < m ? 2 * Q : m);
+  if (2 * Q < m) tail_lu_span<M, K2>(r, rinv, myrd, sing, Gc, tposT, lane, 2 * Q, 3 * Q < m ? 3 * Q : m);
+  if (3 * Q < m) tail_lu_span<M, K3>(r, rinv, myrd, sing, Gc, tposT, lane, 3 * Q, m);
+#else
+  tail_lu_span<M, m>(r, rinv, myrd, sing, Gc, tposT, lane, 0, m);
+#endif
   return __any_sync(FULLMASK, sing && lane < m);
 }
 

@@ -33,6 +33,10 @@
 #ifndef SMEM_OVERLAP
 #define SMEM_OVERLAP (!SMEM_SWEEP_RESIDENT)
 #endif
+// the pivot loop of the register tail LU in four spans with shrinking column counts (0 = one span over all columns)
+#ifndef SMEM_TAIL_SPANS
+#define SMEM_TAIL_SPANS 1
+#endif
 #if SMEM_NC >= 4
 #define SMEM_SCR_GLOBAL 1
 #else

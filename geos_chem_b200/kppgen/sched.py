@@ -43,6 +43,7 @@ import numpy as np
 import os as _os
 LMAX = int(_os.environ.get('GCKPP_LMAX', 8))          # target number of terms per lane before a row is split over more lanes
 SOLVE_LMAX = int(_os.environ.get('GCKPP_SOLVE_LMAX', 7))    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
+BANK_OPT = int(_os.environ.get('GCKPP_BANK_OPT', 1))      # place the terms of a bundle against shared-memory bank conflicts
 TAIL = 32         # tail block size (one lane per tail row)
 NONE = 0xFFFF
 
@@ -103,8 +104,98 @@ class Packer:
             b.pieces = pieces
             b.lw = [meta[l][0] | (len(pieces[l]) << 13) | (maxlen << 19) | (lg << 25) | (meta[l][1] << 28) for l in range(32)]
             assert all(meta[l][0] < 8192 for l in range(32))
+            if BANK_OPT and not (kind & K_DIV):
+                bank_optimize(b)
             self.bundles.append(b)
         self.rounds.append((b0, len(self.bundles), kind))
+
+
+# ---- shared-memory bank model -------------------------------------------------------------------------------------
+# The bundle engine gathers two 8-byte operands per term and cell with one LDS.64 per (term step, cell, operand): all
+# 32 lanes of the instruction use the same array base, so only the lanes' own offsets decide the conflicts.  A 64-bit
+# shared load is served half-warp by half-warp; within a half-warp two lanes collide when their words fall into the
+# same pair of banks ((offset / 8) mod 16) at different addresses, and the instruction takes max-multiplicity
+# wavefronts per half-warp.  ncu of the round-1 kernel: 40 % of all shared-memory wavefronts were such replays and the
+# LSU data pipe was ~50 % busy, so the order in which a lane applies its terms -- free, the sums are re-associated
+# anyway -- is chosen to keep the lanes of a half-warp on different bank pairs (bank_optimize, below).
+def _bp(off):
+    return (off >> 3) & 15
+
+
+def bundle_wavefronts(b):
+    """model: wavefronts of the operand gathers of one bundle and one cell (2 per instruction = conflict-free)"""
+    nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
+    nstep = nch * 4 - 1
+    tot = 0
+    for s in range(nstep):
+        for half in (0, 16):
+            for sh in (16, 0):
+                occ = {}
+                for l in range(half, half + 16):
+                    w = b.pieces[l][s] if s < len(b.pieces[l]) else b.pad
+                    off = (w >> sh) & 0xffff
+                    occ.setdefault(_bp(off), set()).add(off)
+                tot += max(len(v) for v in occ.values())
+    return tot, nstep * 4
+
+
+def bank_optimize(b, passes=3):
+    """Re-place the terms of every lane over the bundle's term steps (positions beyond a lane's own terms hold the no-op
+    pad word) so that, step by step, the lanes of a half-warp hit different bank pairs.  Greedy over the lanes, longest
+    first, each lane an assignment problem (terms x steps) against the lanes already placed; a few refinement passes."""
+    from scipy.optimize import linear_sum_assignment
+    nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
+    nstep = nch * 4 - 1
+    if b.maxlen == 0:
+        return
+    for half in (0, 16):
+        lanes = sorted(range(half, half + 16), key=lambda l: -len(b.pieces[l]))
+        place = {l: None for l in lanes}          # lane -> list of nstep words
+        # occupancy[s][operand][bank pair] -> {offset: count}
+        occ = [[{}, {}] for _ in range(nstep)]
+
+        def add(l, sgn):
+            for s, w in enumerate(place[l]):
+                for o, sh in enumerate((16, 0)):
+                    off = (w >> sh) & 0xffff
+                    d = occ[s][o].setdefault(_bp(off), {})
+                    d[off] = d.get(off, 0) + sgn
+                    if d[off] == 0:
+                        del d[off]
+
+        def cost(w, s):
+            c = 0
+            for o, sh in enumerate((16, 0)):
+                off = (w >> sh) & 0xffff
+                d = occ[s][o].get(_bp(off))
+                if d:
+                    c += len(d) - (1 if off in d else 0)         # distinct other addresses on this bank pair
+            return c
+
+        def assign(l):
+            terms = real[l]
+            out = [b.pad] * nstep
+            if terms:
+                # a step left to the pad word collides like any other address: costs are relative to it
+                padc = np.array([cost(b.pad, s) for s in range(nstep)], np.float64)
+                C = np.array([[cost(w, s) for s in range(nstep)] for w in terms], np.float64) - padc[None, :]
+                ri, ci = linear_sum_assignment(C)
+                for r, c_ in zip(ri, ci):
+                    out[c_] = terms[r]
+            place[l] = out
+
+        real = {l: list(b.pieces[l]) for l in lanes}
+        for l in lanes:
+            assign(l)
+            add(l, +1)
+        for _ in range(passes):
+            for l in lanes:
+                add(l, -1)
+                assign(l)
+                add(l, +1)
+        for l in lanes:
+            b.pieces[l] = place[l]
+    # every lane now carries nstep words (pads included); maxlen is unchanged, so is the chunk count
 
 
 def bundle_chunks(b):
