@@ -245,7 +245,7 @@ extern "C" int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_
 #undef UP
   h->L = make_layout(T);
   h->max_blocks = h->sm_count * h->blocks_per_sm;
-  if (h->next.ensure(sizeof(int)) || h->sums.ensure(64 * sizeof(unsigned long long)) ||
+  if (h->next.ensure(sizeof(int)) || h->sums.ensure(128 * sizeof(unsigned long long)) ||
       h->tol.ensure(2 * sizeof(double) * T->nvar) || h->counter.ensure(4 * sizeof(int))) {
     gckpp_gpu_finalize(h);
     return fail(-1002, "gckpp_gpu_init: out of device memory");
@@ -723,6 +723,11 @@ static void print_profile(gckpp_gpu_handle *h, const unsigned long long *sums)
     fprintf(stderr, "[gckpp profile] block 0 cycles: control %llu fun(x3) %llu jac %llu lu_head %llu lu_tail %llu postlu %llu solve(rest) %llu accept %llu | solve: exec %llu prefetch %llu barrier %llu tails %llu | bundle: fetch+decode %llu terms %llu shuffles %llu write %llu\n",
             sums[8], sums[9], sums[10], sums[11], sums[12], sums[13], sums[14], sums[15], sums[16], sums[17], sums[18], sums[19],
             sums[20], sums[21], sums[22], sums[23]);
+    fprintf(stderr, "[gckpp profile]   lu rounds:");
+    for (int i = 0; i < 24; i++) fprintf(stderr, " %llu", sums[24 + i]);
+    fprintf(stderr, "\n[gckpp profile]   sweep rounds (4 solves):");
+    for (int i = 0; i < 24; i++) fprintf(stderr, " %llu", sums[48 + i]);
+    fprintf(stderr, "\n");
   }
 }
 
@@ -817,7 +822,7 @@ static int check_decoded(gckpp_gpu_handle *h, const Decoded &d)
 
 static int finish_stats(gckpp_gpu_handle *h)
 {
-  unsigned long long sums[64];
+  unsigned long long sums[128];
   CUDA_TRY(cudaMemcpyAsync(sums, h->sums.p, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (getenv("GCKPP_PROFILE")) print_profile(h, sums);
@@ -859,7 +864,7 @@ extern "C" int gckpp_gpu_integrate_device(gckpp_gpu_handle_t *h, int ncell, doub
     CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 128 * sizeof(unsigned long long), h->stream));
   {
     const size_t dw = (size_t)(h->opt_dev_wave > 0 ? h->opt_dev_wave : (1 << 20));
     if (!rconst && h->rconst_work.ensure(sizeof(double) * (size_t)T->nreact * ((size_t)ncell < dw ? (size_t)ncell : dw))) return fail(-1002, "out of device memory for rconst");
@@ -987,7 +992,7 @@ extern "C" int gckpp_gpu_integrate(gckpp_gpu_handle_t *h, int ncell, double tin,
   }
   CUDA_TRY(cudaMemcpyAsync(h->tol.p, atol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->tol.as<double>() + T->nvar, rtol, sizeof(double) * T->nvar, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 64 * sizeof(unsigned long long), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->sums.p, 0, 128 * sizeof(unsigned long long), h->stream));
   // rows x n elements of a [rows][ncell] host array <-> a [rows][n] device array
   auto rows_in = [&](void *dst, const void *src, size_t c0, size_t n, size_t rows, size_t elt) {
     return cudaMemcpy2DAsync(dst, n * elt, (const char *)src + c0 * elt, nc * elt, n * elt, rows, cudaMemcpyHostToDevice, h->s_in);

@@ -47,7 +47,7 @@
 
 // -DSMEM_PROFILE: thread 0 of block 0 accumulates clock64() per phase into sums[8..]
 #ifdef SMEM_PROFILE
-#define PROF_DECL long long pt_ = clock64(), pacc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_DECL long long pt_ = clock64(), pacc_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prl_[24], prs_[24]; for (int i_ = 0; i_ < 24; i_++) prl_[i_] = prs_[i_] = 0;
 #define PROF(i) do { long long t_ = clock64(); pacc_[i] += t_ - pt_; pt_ = t_; } while (0)
 #else
 #define PROF_DECL
@@ -205,11 +205,33 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
     return;
   }
   BPROF(12);
+#if SMEM_EXACT_STEPS
+  // only the bundle's maxlen term steps are applied (warp-uniform switches, one straight-line block per count so the
+  // loads of a chunk still issue back to back): most bundles of the LU and sweep rounds carry one or two terms per
+  // lane, and a pad step costs as many instructions as a real one
+  switch (maxlen < 3 ? maxlen : 3) {
+    case 3: term(c0.y); term(c0.z); term(c0.w); break;
+    case 2: term(c0.y); term(c0.z); break;
+    case 1: term(c0.y); break;
+    default: break;
+  }
+  for (int k0 = 3; k0 < maxlen; k0 += 4) {
+    const uint4 cc = rd.next();
+    const int rem = maxlen - k0;
+    switch (rem < 4 ? rem : 4) {
+      case 4: term(cc.x); term(cc.y); term(cc.z); term(cc.w); break;
+      case 3: term(cc.x); term(cc.y); term(cc.z); break;
+      case 2: term(cc.x); term(cc.y); break;
+      default: term(cc.x); break;
+    }
+  }
+#else
   term(c0.y); term(c0.z); term(c0.w);
   for (int k0 = 3; k0 < maxlen; k0 += 4) {
     const uint4 cc = rd.next();
     term(cc.x); term(cc.y); term(cc.z); term(cc.w);
   }
+#endif
   BPROF(13);
   for (int s = 0; s < lg; s++) {
 #pragma unroll
@@ -634,6 +656,9 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           if (DIR_DIV(d)) stream_round(std::integral_constant<int, OP_LUDIV>(), d);
           else stream_round(std::integral_constant<int, OP_LUUPD>(), d);
           round_barrier(DIR_P(d), warp);
+#ifdef SMEM_PROFILE
+          { long long t_ = clock64(); if (r < 24) prl_[r] += t_ - pt_; pt_ = t_; }
+#endif
         }
         PROF(3);
         auto post_lu_row = [&](int i) {     // singular test (:1985), reciprocal diagonal, U row scaled by it
@@ -784,6 +809,9 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
 #endif
           PROF(8);
           round_barrier(DIR_P(d), warp);
+#ifdef SMEM_PROFILE
+          { long long t_ = clock64(); if (r < 24) prs_[r] += t_ - pt_; }
+#endif
           PROF(10);
         }
 #endif
@@ -871,7 +899,10 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   }
 #ifdef SMEM_PROFILE
   if (tid == 0 && blockIdx.x == 0 && a.sums)
+  {
     for (int i = 0; i < 16; i++) a.sums[8 + i] = (unsigned long long)pacc_[i];
+    for (int i = 0; i < 24; i++) { a.sums[24 + i] = (unsigned long long)prl_[i]; a.sums[48 + i] = (unsigned long long)prs_[i]; }
+  }
 #endif
   if (tid < NC && a.sums) {
     atomicAdd(a.sums + 0, acc_stp);

@@ -43,6 +43,8 @@ import numpy as np
 import os as _os
 LMAX = int(_os.environ.get('GCKPP_LMAX', 8))          # target number of terms per lane before a row is split over more lanes
 SOLVE_LMAX = int(_os.environ.get('GCKPP_SOLVE_LMAX', 7))    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
+EXACT_STEPS = int(_os.environ.get('GCKPP_EXACT_STEPS', 0))  # the kernel applies maxlen steps per bundle (SMEM_EXACT_STEPS), not whole chunks
+BANK_GROUP = int(_os.environ.get('GCKPP_BANK_GROUP', 1))    # ... and choose which items share a half-warp
 BANK_OPT = int(_os.environ.get('GCKPP_BANK_OPT', 1))      # place the terms of a bundle against shared-memory bank conflicts
 TAIL = 32         # tail block size (one lane per tail row)
 NONE = 0xFFFF
@@ -78,6 +80,8 @@ class Packer:
             g = min(32, _pow2ceil((n + lmax - 1) // lmax)) if n > 0 else 1
             its.append((g, -((n + g - 1) // g), row, tw, fl))
         its.sort(key=lambda t: (-t[0], t[1]))
+        if BANK_OPT and BANK_GROUP and not (kind & K_DIV):
+            its = _group_by_banks(its)
         i = 0
         while i < len(its):
             G = its[i][0]
@@ -125,7 +129,7 @@ def _bp(off):
 def bundle_wavefronts(b):
     """model: wavefronts of the operand gathers of one bundle and one cell (2 per instruction = conflict-free)"""
     nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
-    nstep = nch * 4 - 1
+    nstep = b.maxlen if EXACT_STEPS else nch * 4 - 1
     tot = 0
     for s in range(nstep):
         for half in (0, 16):
@@ -145,7 +149,7 @@ def bank_optimize(b, passes=3):
     first, each lane an assignment problem (terms x steps) against the lanes already placed; a few refinement passes."""
     from scipy.optimize import linear_sum_assignment
     nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
-    nstep = nch * 4 - 1
+    nstep = b.maxlen if EXACT_STEPS else nch * 4 - 1
     if b.maxlen == 0:
         return
     for half in (0, 16):
@@ -196,6 +200,59 @@ def bank_optimize(b, passes=3):
         for l in lanes:
             b.pieces[l] = place[l]
     # every lane now carries nstep words (pads included); maxlen is unchanged, so is the chunk count
+
+
+def _group_by_banks(its, window=160):
+    """Order the single-lane items of a round so that the 16 items of every half-warp spread over the bank pairs: the
+    longest remaining item seeds a half-warp, the other 15 come from the next `window` items of the length-sorted list
+    (so a bundle's maxlen barely grows), each chosen for the fewest new (bank pair, address) collisions with the
+    half-warp so far.  Most LU / sweep bundles carry one or two terms per lane -- no freedom inside the lane, all of it
+    in who shares a half-warp.  Items split over several lanes keep their place in front."""
+    head = [t for t in its if t[0] > 1]
+    pool = [t for t in its if t[0] == 1]
+    # lanes left in the bundle the split items end with are filled by the first single-lane items, as before
+    out = list(head)
+    nhead_lanes = sum(t[0] for t in head) % 32
+    if nhead_lanes:
+        k = min(len(pool), 32 - nhead_lanes)
+        out += pool[:k]
+        pool = pool[k:]
+    while pool:
+        seed = pool.pop(0)
+        grp = [seed]
+        occ = [{}, {}]
+
+        def put(t):
+            for w in t[3]:
+                for o, sh in enumerate((16, 0)):
+                    off = (w >> sh) & 0xffff
+                    occ[o].setdefault(_bp(off), set()).add(off)
+
+        def cost(t):
+            c = 0
+            for w in t[3]:
+                for o, sh in enumerate((16, 0)):
+                    off = (w >> sh) & 0xffff
+                    d = occ[o].get(_bp(off))
+                    if d and off not in d:
+                        c += len(d)
+            return c
+
+        put(seed)
+        while len(grp) < 16 and pool:
+            # candidates: the run of items as long as the next one (every extra term step of a bundle is paid by all
+            # its lanes, so lengths are never mixed beyond what the plain sorted order would do)
+            nl = len(pool[0][3])
+            k = 1
+            while k < len(pool) and k < window and len(pool[k][3]) == nl:
+                k += 1
+            win = pool[:k]
+            j = min(range(len(win)), key=lambda q: (cost(win[q]), q))
+            t = pool.pop(j)
+            grp.append(t)
+            put(t)
+        out += grp
+    return out
 
 
 def bundle_chunks(b):
@@ -384,7 +441,8 @@ class Schedule:
             assert ch.shape[0] == 1 + max(0, (maxlen + 0) // 4 if maxlen > 3 else 0) or True
             acc = np.zeros(32)
             first = ((words[:, 1] & 0xffff) >> 3).astype(np.int64) if words.shape[1] > 1 else np.zeros(32, np.int64)
-            nterm = words.shape[1] - 1            # the kernel applies every word of every chunk (padding is a no-op)
+            # the kernel applies maxlen term steps (EXACT_STEPS) or every word of every chunk (padding is a no-op)
+            nterm = min(maxlen, words.shape[1] - 1) if EXACT_STEPS else words.shape[1] - 1
             for k in range(nterm if op not in ("div",) else 0):
                 w = words[:, 1 + k]
                 hi = ((w >> 16) >> 3).astype(np.int64)
