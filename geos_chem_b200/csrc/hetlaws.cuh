@@ -235,7 +235,8 @@ __device__ __forceinline__ double het_OHuptkBySALCCl(const MetCell &m, const Het
 //   Gam_HOBr_Aer / _Cld / _Ice + HOBrUptkBy* :1505-2032; Gam_HOCl_Cld / _Aer + HOClUptkBy* :2072-2335
 //   IONO2uptkByH2O :2544-2577; N2O5uptkByCloud / ByStratHCl :2881-2922; NO2 / NO3uptk1stOrdAndCloud :2928-3058
 //   Gam_NO3 + NO3hypsisClonSALA / SALC :2982-3100; Gamma_O3_Br + O3uptkBy* :3106-3238
-// Not here: N2O5uptkByH2O / BySALACl / BySALCCl (N2O5_InorgOrg) and K_MT / K_CLD.
+//   N2O5_InorgOrg + N2O5uptkByH2O / BySALACl / BySALCCl :2583-2879 (at the end of this file)
+// Not here: K_MT / K_CLD and the SRHOBr / SRHOCl sums (the sulfur module).
 struct HetCell2 {
   double natSurface, TurnOffHetRates, CldFr, aIce, aLiq, rIce, rLiq, pHCloud, pHSSA[2];
   double Cl_conc_Cld, Br_conc_Cld, Br_conc_SSA, Br_conc_SSC, Br_over_Cl_Cld, Br_over_Cl_SSA, Br_over_Cl_SSC;
@@ -259,8 +260,22 @@ __device__ __forceinline__ HetCell2 het_load2(const double *__restrict__ het, si
 enum { SLA_N2O5_H2O = 0, SLA_N2O5_HCl, SLA_ClNO3_H2O, SLA_ClNO3_HCl, SLA_ClNO3_HBr, SLA_BrNO3_H2O, SLA_BrNO3_HCl,
        SLA_HOCl_HCl, SLA_HOCl_HBr, SLA_HOBr_HCl, SLA_HOBr_HBr };
 
+// third block: what N2O5_InorgOrg reads (wet volumes and water contents of the sulfate / organic / sea-salt aerosol,
+// OM/OC ratios)
+struct HetCell3 { double AClVol, xVol_ORC, xVol_SSC, xH2O_SUL, xH2O_ORC, xH2O_SSC, OMOC_POA, OMOC_OPOA; };
+#define GCKPP_NHET_FIELDS3 8
+static_assert(sizeof(HetCell3) == GCKPP_NHET_FIELDS3 * sizeof(double), "HetCell3 must be 8 doubles");
+__device__ __forceinline__ HetCell3 het_load3(const double *__restrict__ het, size_t stride)
+{
+  HetCell3 K;
+  double *p = reinterpret_cast<double *>(&K);
+#pragma unroll
+  for (int k = 0; k < GCKPP_NHET_FIELDS3; k++) p[k] = het[(size_t)(GCKPP_NHET_FIELDS + GCKPP_NHET_FIELDS2 + k) * stride];
+  return K;
+}
+
 struct HetCtx {
-  const MetCell &m; const HetCell &H; const HetCell2 &G;
+  const MetCell &m; const HetCell &H; const HetCell2 &G; const HetCell3 &K;
   const double *srmw, *mw, *hk0, *hcr, *conc; size_t stride;
   __device__ __forceinline__ double C(int i) const { return conc[(size_t)i * stride]; }
   __device__ __forceinline__ double Ars(double area, double radius, double gamma, double srMw) const { return het_Ars_L1k(m, area, radius, gamma, srMw); }
@@ -867,3 +882,94 @@ __device__ __forceinline__ double het_O3uptkByBrSAL(const HetCtx &x, bool coarse
 }
 __device__ __forceinline__ double het2_O3uptkByBrSALA(const HetCtx &x) { return het_O3uptkByBrSAL(x, false); }
 __device__ __forceinline__ double het2_O3uptkByBrSALC(const HetCtx &x) { return het_O3uptkByBrSAL(x, true); }
+
+// ---- N2O5 on aerosol with an organic coating (McDuffie 2018 / Bertram & Thornton 2009): N2O5_InorgOrg :2699-2858,
+//      ClNO2_BT :2860-2879, N2O5uptkByH2O :2583-2641, N2O5uptkBySALACl :2643-2670, N2O5uptkBySALCCl :2672-2697
+#define HET_AVO 6.022140857e+23
+__device__ __forceinline__ double het_ClNO2_BT(double Cl, double H2O)
+{
+  const double k2k3 = 1.0 / 4.5e+2;
+  if (H2O < 0.1) return (Cl > 1e-3) ? 1.0 : 0.0;
+  return 1.0 / (1.0 + k2k3 * het_SafeDiv(H2O, Cl, 1.0e+30));
+}
+struct N2O5IO { double gamma, Y_ClNO2, Rp, areaTotal; };
+__device__ __forceinline__ N2O5IO het_N2O5_InorgOrg(const HetCtx &x, double volInorg, double volOrg, double H2Oinorg, double H2Oorg,
+                                                    double Rcore, double NIT, double Cl)
+{
+  const double KH = 5.1e+1, k3k2b = 4.0e-2, beta = 1.15e+6, delta = 1.3e-1, Haq = 5e+3, Daq = 1e-9, ONE_THIRD = 1.0 / 3.0;
+  N2O5IO r;
+  const double volTotal = volInorg + volOrg, H2Ototal = H2Oinorg + H2Oorg;
+  const double volRatioDry = het_SafeDiv(fmax(volInorg - H2Oinorg, 0.0), fmax(volTotal - H2Ototal, 0.0), 0.0);
+  r.Rp = het_SafeDiv(Rcore, pow(volRatioDry, ONE_THIRD), Rcore);
+  const double l = r.Rp - Rcore;
+  double speed = sqrt(x.m.EIGHT_RSTARG_T / (HET_PI * (x.mw[HETIND_N2O5] * 1.0e-3)));
+  const double M_H2O = H2Ototal / 18e+0 / volTotal * 1000.0;
+  const double M_NIT = NIT / volTotal / HET_AVO * 1000.0;
+  const double M_Cl = Cl / volTotal / HET_AVO * 1000.0;
+  const double OCratio = (((x.K.OMOC_POA + x.K.OMOC_OPOA) / 2.0) - 1.17) / 1.29;
+  const double eps = 1.5e-1 * OCratio + 1.6e-3 * x.m.RELHUM;
+  double gamma_coat, gamma_core;
+  if (l <= 0.0) gamma_coat = 0.0;
+  else gamma_coat = (x.m.FOUR_RGASLATM_T * 1.0e-3 * eps * Haq * Daq * Rcore / 100.0) / (speed * l / 100.0 * r.Rp / 100.0);
+  r.areaTotal = 3.0 * volTotal / r.Rp;
+  if (M_H2O < 0.1) {
+    gamma_core = 0.005;
+  } else {
+    speed = speed * 1e+2;
+    double A = ((4.0 * volTotal) / (speed * r.areaTotal)) * KH;
+    A = fmin(A, 3.2e-8);
+    double k2f;
+    if (delta * M_H2O < 1e-2) k2f = beta * (delta * M_H2O);
+    else k2f = beta * (1e+0 - exp(-delta * M_H2O));
+    gamma_core = A * k2f * (1.0 - 1.0 / (1.0 + het_SafeDiv(k3k2b * M_H2O, M_NIT, 1.0e+30)));
+  }
+  if (gamma_coat <= 0.0) r.gamma = gamma_core;
+  else if (gamma_core <= 0.0) r.gamma = 0.0;
+  else r.gamma = 1.0 / ((1.0 / gamma_core) + (1.0 / gamma_coat));
+  r.Y_ClNO2 = het_ClNO2_BT(M_Cl, M_H2O);
+  return r;
+}
+__device__ __forceinline__ N2O5IO het_N2O5_fine(const HetCtx &x)
+{
+  return het_N2O5_InorgOrg(x, x.K.AClVol, x.K.xVol_ORC, x.K.xH2O_SUL, x.K.xH2O_ORC, x.H.aClRadi, x.C(HETIND_NIT), x.C(HETIND_SALACL));
+}
+__device__ __forceinline__ N2O5IO het_N2O5_coarse(const HetCtx &x)
+{
+  return het_N2O5_InorgOrg(x, x.K.xVol_SSC, 0.0, x.K.xH2O_SSC, 0.0, x.H.xRadi[HA_SSC], x.C(HETIND_NITs), x.C(HETIND_SALCCL));
+}
+__device__ __forceinline__ double het2_N2O5uptkByH2O(const HetCtx &x)
+{
+  const HetCell &H = x.H; const HetCell2 &G = x.G;
+  double k = 0.0, ktmp;
+  const double srMw = x.srmw[HETIND_N2O5];
+#pragma unroll
+  for (int a = HA_DU1; a < HA_SUL; a++) k = k + x.Ars(H.ClearFr * H.xArea[a], H.xRadi[a], 0.02, srMw);
+  N2O5IO r = het_N2O5_fine(x);
+  ktmp = x.Ars(H.ClearFr * r.areaTotal, r.Rp, r.gamma, srMw);
+  k = k + ktmp - (ktmp * r.Y_ClNO2 * 0.25);
+  k = k + x.Ars(H.ClearFr * H.xArea[HA_BKC], H.xRadi[HA_BKC], 0.005, srMw);
+  r = het_N2O5_coarse(x);
+  ktmp = x.Ars(H.ClearFr * r.areaTotal, r.Rp, r.gamma, srMw);
+  k = k + ktmp - (ktmp * r.Y_ClNO2);
+  k = k + H.xArea[HA_SLA] * G.KHETI_SLA[SLA_N2O5_H2O];
+  double gamma = 0.02;
+  if (G.natSurface != 0.0) gamma = 4.0e-4;
+  k = k + x.Ars(H.ClearFr * H.xArea[HA_IIC], H.xRadi[HA_IIC], gamma, srMw);
+  return het_kIIR1Ltd(x.C(HETIND_N2O5), x.C(HETIND_H2O), k);
+}
+__device__ __forceinline__ double het2_N2O5uptkBySALACl(const HetCtx &x)
+{
+  if (x.H.stratBox != 0.0) return 0.0;
+  const N2O5IO r = het_N2O5_fine(x);
+  double k = x.Ars(x.H.ClearFr * r.areaTotal, r.Rp, r.gamma, x.srmw[HETIND_N2O5]);
+  k = k * r.Y_ClNO2 * 0.25;
+  return het_kIIR1Ltd(x.C(HETIND_N2O5), x.C(HETIND_SALACL), k);
+}
+__device__ __forceinline__ double het2_N2O5uptkBySALCCl(const HetCtx &x)
+{
+  if (x.H.stratBox != 0.0) return 0.0;
+  const N2O5IO r = het_N2O5_coarse(x);
+  double k = x.Ars(x.H.ClearFr * r.areaTotal, r.Rp, r.gamma, x.srmw[HETIND_N2O5]);
+  k = k * r.Y_ClNO2;
+  return het_kIIR1Ltd(x.C(HETIND_N2O5), x.C(HETIND_SALCCL), k);
+}

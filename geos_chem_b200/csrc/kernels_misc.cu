@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(128) update_rconst_kernel(int ncell, int strid
     const HetCell H = het_load(het + cell, (size_t)stride);
     if (nspec_data > 0) {
       const HetCell2 G = het_load2(het + cell, (size_t)stride);
-      const HetCtx X{m, H, G, srmw, srmw + nspec_data, srmw + 2 * nspec_data, srmw + 3 * nspec_data, conc + cell, (size_t)stride};
+      const HetCell3 K3 = het_load3(het + cell, (size_t)stride);
+      const HetCtx X{m, H, G, K3, srmw, srmw + nspec_data, srmw + 2 * nspec_data, srmw + 3 * nspec_data, conc + cell, (size_t)stride};
       fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw, &X);
     } else {
       fullchem_update_rconst_cell(m, ph, kh, rconst + cell, (size_t)stride, (size_t)ostride, &H, conc + cell, srmw, nullptr);

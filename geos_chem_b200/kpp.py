@@ -331,8 +331,8 @@ class KppSolver:
         return x
 
     # ------------------------------------------------------------------ heterogeneous laws on the device
-    NHET = 96
-    # rows 0-47: first part; rows 48-95: second part (read only after set_species_data); order = include/gckpp_gpu.h
+    NHET = 104
+    # rows 0-47: first part; rows 48-103: second part (read only after set_species_data); order = include/gckpp_gpu.h
     HET_FIELDS = ("SUNCOS", "stratBox", "SSA_is_Alk", "SSA_is_Acid", "SSC_is_Alk", "SSC_is_Acid", "f_Alk_SSA", "f_Alk_SSC",
                   "f_Acid_SSA", "f_Acid_SSC", "ClearFr", "aClArea", "aClRadi", "Cl_conc_SSA", "Cl_conc_SSC", "gamma_HO2",
                   "H_PLUS", "NO3_molal", "SO4_molal", "HSO4_molal") + tuple("xArea%d" % k for k in range(1, 15)) + \
@@ -341,7 +341,8 @@ class KppSolver:
          "Cl_conc_Cld", "Br_conc_Cld", "Br_conc_SSA", "Br_conc_SSC", "Br_over_Cl_Cld", "Br_over_Cl_SSA", "Br_over_Cl_SSC",
          "frac_Br_CldA", "frac_Br_CldC", "frac_Br_CldG", "frac_Cl_CldA", "frac_Cl_CldC", "frac_Cl_CldG", "frac_SALACL",
          "frac_HSO3_aq", "HSO3m", "HCl_theta", "HBr_theta", "HNO3_theta", "H_conc_LCl", "H_conc_SSA", "H_conc_SSC",
-         "HSO3_aq", "SO3_aq", "TSO3_aq", "aWater1", "aWater2") + tuple("KHETI_SLA%d" % k for k in range(1, 12))
+         "HSO3_aq", "SO3_aq", "TSO3_aq", "aWater1", "aWater2") + tuple("KHETI_SLA%d" % k for k in range(1, 12)) + \
+        ("AClVol", "xVol_ORC", "xVol_SSC", "xH2O_SUL", "xH2O_ORC", "xH2O_SSC", "OMOC_POA", "OMOC_OPOA")
 
     def set_species_data(self, sr_mw, mw, henry_k0, henry_cr):
         """set_sr_mw plus MW, HENRY_K0, HENRY_CR (1:NSPEC) of gckpp_Global: switches the second part of the device-side

@@ -1,6 +1,8 @@
 #!/bin/bash
-o=gpurun_out/r02ak; mkdir -p $o
-for v in lmax7 lmax11 lmax4 solve3 solve11; do
-( GCKPP_B200_LIB=$PWD/geos_chem_b200/libgckpp_b200_$v.so VB_ITERS=3 timeout 300 python tools/variant_bench.py own ) > $o/variant_$v.log 2>&1; echo $v; tail -n 1 $o/variant_$v.log
-done
-( VB_ITERS=3 timeout 300 python tools/variant_bench.py own ) > $o/variant_default.log 2>&1; tail -n 1 $o/variant_default.log
+bash tools/gpu_round.sh r02al
+o=gpurun_out/r02al
+( timeout 600 python bench.py --config 1 --steps 3 --warmup 3 --no-cpu-baseline ) > $o/bench_config1.log 2>&1; tail -n 1 $o/bench_config1.log | cut -c1-200
+( timeout 600 python bench.py --hstart cold --steps 2 --warmup 3 --no-cpu-baseline ) > $o/bench_cold.log 2>&1; tail -n 1 $o/bench_cold.log | cut -c1-200
+( timeout 600 python bench.py --config 5-hg --steps 3 --warmup 3 ) > $o/bench_hg.log 2>&1; tail -n 1 $o/bench_hg.log | cut -c1-200
+( timeout 600 python bench.py --config 5-carbon --steps 3 --warmup 3 ) > $o/bench_carbon.log 2>&1; tail -n 1 $o/bench_carbon.log | cut -c1-200
+( timeout 900 python bench.py --config 5-ar --steps 3 --warmup 3 ) > $o/bench_ar.log 2>&1; tail -n 1 $o/bench_ar.log | cut -c1-200

@@ -144,13 +144,16 @@ enum {
   GCKPP_HET_FRAC_CL_CLDG, GCKPP_HET_FRAC_SALACL, GCKPP_HET_FRAC_HSO3_AQ, GCKPP_HET_HSO3M, GCKPP_HET_HCL_THETA,
   GCKPP_HET_HBR_THETA, GCKPP_HET_HNO3_THETA, GCKPP_HET_H_CONC_LCL, GCKPP_HET_H_CONC_SSA, GCKPP_HET_H_CONC_SSC,
   GCKPP_HET_HSO3_AQ, GCKPP_HET_SO3_AQ, GCKPP_HET_TSO3_AQ, GCKPP_HET_AWATER /* (1:2) */, GCKPP_HET_KHETI_SLA = 85 /* (1:11) */,
-  GCKPP_NHET = 96
+  /* what N2O5_InorgOrg reads: AClVol, xVol(ORC), xVol(SSC), xH2O(SUL), xH2O(ORC), xH2O(SSC), OMOC_POA, OMOC_OPOA */
+  GCKPP_HET_ACLVOL = 96, GCKPP_HET_XVOL_ORC, GCKPP_HET_XVOL_SSC, GCKPP_HET_XH2O_SUL, GCKPP_HET_XH2O_ORC, GCKPP_HET_XH2O_SSC,
+  GCKPP_HET_OMOC_POA, GCKPP_HET_OMOC_OPOA,
+  GCKPP_NHET = 104
 };
 int gckpp_gpu_set_sr_mw(gckpp_gpu_handle_t *handle, int n, const double *sr_mw);
 /* set_sr_mw plus MW(1:NSPEC) [g/mol] and the Henry's-law constants HENRY_K0 [M/atm], HENRY_CR [K] of gckpp_Global: enables
- * the second part -- 35 more constants (BrNO3, ClNO2, ClNO3, HOBr, HOCl, IONO2, O3 + bromide, NO2 / NO3 uptake and cloud
- * loss, NO3 on sea-salt chloride, N2O5 in cloud / + stratospheric HCl; fullchem_RateLawFuncs.F90:803-3238).  17 constants
- * then remain external: K_MT(6), K_CLD(6), the three N2O5 laws that use N2O5_InorgOrg and the two HSO3m / SO3mm sums
+ * the second part -- 38 more constants (BrNO3, ClNO2, ClNO3, HOBr, HOCl, IONO2, N2O5, O3 + bromide, NO2 / NO3 uptake and cloud
+ * loss, NO3 on sea-salt chloride, N2O5 on aerosol / in cloud / + stratospheric HCl; fullchem_RateLawFuncs.F90:803-3238).  14 constants
+ * then remain external: K_MT(6), K_CLD(6) and the two HSO3m / SO3mm sums
  * that add the sulfur module's SRHOCl / SRHOBr. */
 int gckpp_gpu_set_species_data(gckpp_gpu_handle_t *handle, int n, const double *sr_mw, const double *mw,
                                const double *henry_k0, const double *henry_cr);

@@ -1006,7 +1006,108 @@ def O3uptkByBrSALC(c, ind):
     return kIIR1Ltd(c.C[ind["O3"]], c.C[ind["BrSALC"]], k)
 
 
-LAWS2 = {f.__name__: f for f in (
+AVO = 6.022140857e+23
+FOUR_RGASLATM = 4.0 * RGASLATM
+
+
+def ClNO2_BT(Cl, H2O):
+    k2k3 = 1.0 / 4.5e+2
+    if H2O < 0.1:
+        phi = 0.0
+        if Cl > 1e-3:
+            phi = 1.0
+        return phi
+    return 1.0 / (1.0 + k2k3 * safe_div(H2O, Cl, 1.0e+30))
+
+
+def N2O5_InorgOrg(c, ind, volInorg, volOrg, H2Oinorg, H2Oorg, Rcore, NIT, Cl):
+    """-> gamma, Y_ClNO2, Rp, areaTotal  (fullchem_RateLawFuncs.F90:2699-2858)"""
+    KH, k3k2b, beta, delta = 5.1e+1, 4.0e-2, 1.15e+6, 1.3e-1
+    Haq, Daq, ONE_THIRD = 5e+3, 1e-9, 1.0 / 3.0
+    volTotal = volInorg + volOrg
+    H2Ototal = H2Oinorg + H2Oorg
+    volRatioDry = safe_div(max(volInorg - H2Oinorg, 0.0), max(volTotal - H2Ototal, 0.0), 0.0)
+    Rp = safe_div(Rcore, volRatioDry ** ONE_THIRD, Rcore)
+    l = Rp - Rcore
+    M_N2O5 = c.MW[ind["N2O5"]] * 1.0e-3
+    speed = math.sqrt(c.EIGHT_RSTARG_T / (PI * M_N2O5))
+    M_H2O = H2Ototal / 18e+0 / volTotal * 1000.0
+    M_NIT = NIT / volTotal / AVO * 1000.0
+    M_Cl = Cl / volTotal / AVO * 1000.0
+    OCratio = (((c.OMOC_POA + c.OMOC_OPOA) / 2.0) - 1.17) / 1.29
+    eps = 1.5e-1 * OCratio + 1.6e-3 * c.RELHUM
+    if l <= 0.0e+0:
+        gamma_coat = 0.0
+    else:
+        gamma_coat = (c.FOUR_RGASLATM_T * 1.0e-3 * eps * Haq * Daq * Rcore / 100.0) / (speed * l / 100.0 * Rp / 100.0)
+    areaTotal = 3.0 * volTotal / Rp
+    if M_H2O < 0.1:
+        gamma_core = 0.005
+    else:
+        speed = speed * 1e+2
+        A = ((4.0 * volTotal) / (speed * areaTotal)) * KH
+        A = min(A, 3.2e-8)
+        if delta * M_H2O < 1e-2:
+            k2f = beta * (delta * M_H2O)
+        else:
+            k2f = beta * (1e+0 - math.exp(-delta * M_H2O))
+        gamma_core = A * k2f * (1.0 - 1.0 / (1.0 + safe_div(k3k2b * M_H2O, M_NIT, 1.0e+30)))
+    if gamma_coat <= 0.0:
+        gamma = gamma_core
+    elif gamma_core <= 0.0:
+        gamma = 0.0
+    else:
+        gamma = 1.0 / ((1.0 / gamma_core) + (1.0 / gamma_coat))
+    return gamma, ClNO2_BT(M_Cl, M_H2O), Rp, areaTotal
+
+
+def N2O5uptkByH2O(c, ind):
+    k = 0.0
+    srMw = c.SR_MW[ind["N2O5"]]
+    gamma = 0.02
+    for a in range(DU1, DU1 + 7):
+        k = k + c.ars_l1k(c.ClearFr * c.xArea[a], c.xRadi[a], gamma, srMw)
+    gamma, Y_ClNO2, Rp, SA = N2O5_InorgOrg(c, ind, c.AClVol, c.xVol_ORC, c.xH2O_SUL, c.xH2O_ORC, c.aClRadi,
+                                           c.C[ind["NIT"]], c.C[ind["SALACL"]])
+    ktmp = c.ars_l1k(c.ClearFr * SA, Rp, gamma, srMw)
+    k = k + ktmp - (ktmp * Y_ClNO2 * 0.25)
+    gamma = 0.005
+    k = k + c.ars_l1k(c.ClearFr * c.xArea[BKC], c.xRadi[BKC], gamma, srMw)
+    gamma, Y_ClNO2, Rp, SA = N2O5_InorgOrg(c, ind, c.xVol_SSC, 0.0, c.xH2O_SSC, 0.0, c.xRadi[SSC],
+                                           c.C[ind["NITs"]], c.C[ind["SALCCL"]])
+    ktmp = c.ars_l1k(c.ClearFr * SA, Rp, gamma, srMw)
+    k = k + ktmp - (ktmp * Y_ClNO2)
+    k = k + c.xArea[SLA] * c.KHETI_SLA[N2O5_plus_H2O]
+    gamma = 0.02
+    if c.natSurface:
+        gamma = 4.0e-4
+    k = k + c.ars_l1k(c.ClearFr * c.xArea[IIC], c.xRadi[IIC], gamma, srMw)
+    return kIIR1Ltd(c.C[ind["N2O5"]], c.C[ind["H2O"]], k)
+
+
+def N2O5uptkBySALACl(c, ind):
+    k = 0.0
+    if c.stratBox:
+        return k
+    gamma, Y_ClNO2, Rp, SA = N2O5_InorgOrg(c, ind, c.AClVol, c.xVol_ORC, c.xH2O_SUL, c.xH2O_ORC, c.aClRadi,
+                                           c.C[ind["NIT"]], c.C[ind["SALACL"]])
+    k = c.ars_l1k(c.ClearFr * SA, Rp, gamma, c.SR_MW[ind["N2O5"]])
+    k = k * Y_ClNO2 * 0.25
+    return kIIR1Ltd(c.C[ind["N2O5"]], c.C[ind["SALACL"]], k)
+
+
+def N2O5uptkBySALCCl(c, ind):
+    k = 0.0
+    if c.stratBox:
+        return k
+    gamma, Y_ClNO2, Rp, SA = N2O5_InorgOrg(c, ind, c.xVol_SSC, 0.0, c.xH2O_SSC, 0.0, c.xRadi[SSC],
+                                           c.C[ind["NITs"]], c.C[ind["SALCCL"]])
+    k = c.ars_l1k(c.ClearFr * SA, Rp, gamma, c.SR_MW[ind["N2O5"]])
+    k = k * Y_ClNO2
+    return kIIR1Ltd(c.C[ind["N2O5"]], c.C[ind["SALCCL"]], k)
+
+
+LAWS2 = {f.__name__: f for f in (N2O5uptkByH2O, N2O5uptkBySALACl, N2O5uptkBySALCCl,
     BrNO3uptkByH2O, BrNO3uptkByHCl, ClNO2uptkByBrSALA, ClNO2uptkByBrSALC, ClNO2uptkByHBr, ClNO2uptkBySALACL,
     ClNO2uptkBySALCCL, ClNO2uptkByHCl, ClNO3uptkByH2O, ClNO3uptkByHCl, ClNO3uptkByHBr, ClNO3uptkByBrSALA,
     ClNO3uptkByBrSALC, ClNO3uptkBySALACL, ClNO3uptkBySALCCL, HOBrUptkByHBr, HOBrUptkByHCl, HOBrUptkByBrSALA,

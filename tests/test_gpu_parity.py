@@ -559,7 +559,7 @@ def test_heterogeneous_laws_on_device_vs_oracle(solver, oracle):
 @pytest.mark.gpu
 def test_heterogeneous_laws_second_part_vs_oracle(solver, oracle):
     """SURVEY 8 f1, second part: with the species data (SR_MW, MW, HENRY_K0, HENRY_CR) and the 96 HetState fields,
-    Update_RCONST also evaluates the cloud / halogen uptake laws (35 more constants: BrNO3, ClNO2, ClNO3, HOBr, HOCl,
+    Update_RCONST also evaluates the cloud / halogen uptake laws (38 more constants: BrNO3, ClNO2, ClNO3, HOBr, HOCl,
     IONO2, N2O5 in cloud / + stratospheric HCl, NO2 / NO3 uptake, NO3 on sea-salt chloride, O3 + bromide;
     fullchem_RateLawFuncs.F90:803-3238).  GPU against the scalar Python restatement of the Fortran
     (oracle/het_oracle.py): rounding level for 99.9 % of the entries, 1e-8 at worst (libm differences pass through the
@@ -574,7 +574,7 @@ def test_heterogeneous_laws_second_part_vs_oracle(solver, oracle):
     sub = lambda a: np.ascontiguousarray(a[..., idx])
     temp, numden, h2o, photol, khet, conc = map(sub, (g["temp"], g["numden"], g["h2o"], g["photol"], g["khet"], g["conc"]))
     F = kpp.KppSolver.HET_FIELDS
-    assert len(F) == kpp.KppSolver.NHET == 96
+    assert len(F) == kpp.KppSolver.NHET == 104
     het = np.zeros((kpp.KppSolver.NHET, n))
     col = {name: k for k, name in enumerate(F)}
     logu = lambda lo, hi: 10 ** rng.uniform(lo, hi, n)
@@ -615,6 +615,12 @@ def test_heterogeneous_laws_second_part_vs_oracle(solver, oracle):
     for k in range(1, 15):
         het[col["xArea%d" % k]] = some0(logu(-10, -6), 0.15)
         het[col["xRadi%d" % k]] = logu(-6.5, -3.5)
+    # N2O5_InorgOrg: wet volumes with a water share on both sides of 0.1 mol/L, with and without an organic coating
+    for v, w in (("AClVol", "xH2O_SUL"), ("xVol_ORC", "xH2O_ORC"), ("xVol_SSC", "xH2O_SSC")):
+        het[col[v]] = logu(-13, -10)
+        het[col[w]] = het[col[v]] * np.where(rng.uniform(size=n) < 0.2, 10 ** rng.uniform(-6, -3, n), rng.uniform(0.05, 0.9, n))
+    het[col["xVol_ORC"]] = some0(het[col["xVol_ORC"]], 0.3); het[col["xH2O_ORC"]] = np.minimum(het[col["xH2O_ORC"]], het[col["xVol_ORC"]])
+    het[col["OMOC_POA"]] = rng.uniform(1.2, 2.2, n); het[col["OMOC_OPOA"]] = rng.uniform(1.8, 2.4, n)
     h2o = h2o * 10 ** rng.uniform(-0.5, 1.0, n)
     mw = rng.uniform(17.0, 300.0, m.nspec)
     sr_mw = np.sqrt(mw)
@@ -624,7 +630,7 @@ def test_heterogeneous_laws_second_part_vs_oracle(solver, oracle):
     want1 = [ho.evaluate(m.rconst, m.ind, cl) for cl in cells]
     want2 = [ho.evaluate2(m.rconst, m.ind, cl, mw, hk0, hcr) for cl in cells]
     rows1, rows2 = sorted(want1[0]), sorted(want2[0])
-    assert len(rows1) == 61 and len(rows2) == 35 and not set(rows1) & set(rows2)
+    assert len(rows1) == 61 and len(rows2) == 38 and not set(rows1) & set(rows2)
     ref = oracle.update_rconst("fullchem", temp, numden, h2o, photol, khet)
     exp = ref.copy()
     for c in range(n):

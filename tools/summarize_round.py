@@ -7,8 +7,8 @@ r = json.loads([x for x in open(src + "bench_ref.log") if x.startswith("{")][-1]
 print("value %.0f cells/s  %.1f ms/step  e2e %.0f  cpu_baseline %.0f (%d cores)  reference arm %.0f (%d cores)" % (
     d["value"], d["ms_per_step"], d["e2e"]["value"], d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"],
     r["value"], r["cpu_baseline"]["cores"]))
-print("roofline hbm frac %.3e  fp64 frac %.4f  kernel_ms %.1f  launches %d" % (
-    d["roofline"]["frac"], d["roofline"]["fp64"]["frac"], d["roofline"]["kernel_ms"], d["gpu_launches"]))
+print("roofline fp64 frac %.4f  hbm frac %.3e  kernel_ms %.1f  launches %d" % (
+    d["roofline"]["frac"], d["roofline"]["hbm"]["frac"], d["roofline"]["kernel_ms"], d["gpu_launches"]))
 rows = list(csv.reader(open(src + "ros_full_raw.csv")))
 dd = {h: (v, u) for h, u, v in zip(rows[0], rows[1], rows[2])}
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
