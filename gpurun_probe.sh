@@ -1,8 +1,6 @@
 #!/bin/bash
-bash tools/gpu_round.sh r02al
-o=gpurun_out/r02al
-( timeout 600 python bench.py --config 1 --steps 3 --warmup 3 --no-cpu-baseline ) > $o/bench_config1.log 2>&1; tail -n 1 $o/bench_config1.log | cut -c1-200
-( timeout 600 python bench.py --hstart cold --steps 2 --warmup 3 --no-cpu-baseline ) > $o/bench_cold.log 2>&1; tail -n 1 $o/bench_cold.log | cut -c1-200
-( timeout 600 python bench.py --config 5-hg --steps 3 --warmup 3 ) > $o/bench_hg.log 2>&1; tail -n 1 $o/bench_hg.log | cut -c1-200
-( timeout 600 python bench.py --config 5-carbon --steps 3 --warmup 3 ) > $o/bench_carbon.log 2>&1; tail -n 1 $o/bench_carbon.log | cut -c1-200
-( timeout 900 python bench.py --config 5-ar --steps 3 --warmup 3 ) > $o/bench_ar.log 2>&1; tail -n 1 $o/bench_ar.log | cut -c1-200
+o=gpurun_out/r02am; mkdir -p $o
+( time timeout 1200 python -m pytest tests -m gpu -x -q -s -k "heterogeneous" ) > $o/pytest_het.log 2>&1; grep -E "device het|passed|failed|Error|^E " $o/pytest_het.log | head
+( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 2 --warmup 3 ) > $o/bench_n2.log 2>&1; grep '^{' $o/bench_n2.log | tail -n 1 | cut -c1-700
+( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 ) > $o/bench_ref_n2.log 2>&1; grep '^{' $o/bench_ref_n2.log | tail -n 1 | cut -c1-500
+( timeout 600 python -m pytest tests -m gpu -x -q -k "two_dev or two_gpu or devices" ) > $o/pytest_2gpu.log 2>&1; tail -n 3 $o/pytest_2gpu.log
