@@ -57,17 +57,21 @@ const char *gckpp_gpu_spc_name(int mech_id, int i);
 int gckpp_gpu_init(int mech_id, int device, int max_cells, gckpp_gpu_handle_t **handle);
 int gckpp_gpu_finalize(gckpp_gpu_handle_t *handle);
 
-/* Options (integer-valued):
+/* Options (integer-valued; an unknown key returns -10):
  *   "retry"      1 = on IERR<0 redo the cell once with Hstart=0 from the saved
  *                concentrations (Do_FullChem's policy, fullchem_mod.F90:1138-1162); default 0
- *   "kernel"     0 = table-driven one-cell-per-lane kernel that keeps the reference's operation order
- *                (bit-identical step sequences with the CPU restatement, any ICNTRL(3) method);
- *                1 = shared-memory-resident Rodas3 kernel (default for fullchem and Hg with
- *                ICNTRL(3) = 0 or 4; sums re-associated, FMA contraction, rounding-level differences)
- *   "chunks"     host-buffer entry only: number of contiguous cell ranges whose host<->device copies are
- *                overlapped with the integration of the neighbouring ranges (default 4; 1 = one serial pass).
- *                Not used with an `active` mask or with "retry".
- *   "sort"       1 = visit cells in descending previous-step cost (hstart ascending); default 0
+ *   "kernel"     -1 = choose (default): the shared-memory block kernel for fullchem with ICNTRL(3) = 0 or 4 (Rodas3), with or
+ *                without auto-reduce; the unrolled one-cell-per-thread kernel for Hg; the table-driven kernel otherwise;
+ *                0 = table-driven one-cell-per-lane kernel that keeps the reference's operation order
+ *                (bit-identical step sequences with the CPU restatement, any ICNTRL(3) method, auto-reduce);
+ *                1 = shared-memory-resident Rodas3 block kernel (sums re-associated, FMA contraction, rounding-level
+ *                differences); 2 = warp-group kernel (results vary run to run at 1e-9: on request only);
+ *                3 = lane kernel (one cell per lane, streamed workspace, every method); 4 = unrolled kernel (Hg)
+ *   "wave_cells"        host-buffer entry: cells per wave (0 = choose from the free device memory); the copies of a wave
+ *                       overlap the integration of its neighbours
+ *   "device_wave_cells" device entry without rate constants: cells per Update_RCONST wave (bounds the RCONST scratch)
+ *   "pin"        1 = page-lock the caller's pageable host arrays for the duration of the call
+ *   "blocks_per_sm", "blocks_cap", "threads", "chunks"   launch-shape knobs of the table-driven kernel and test hooks
  */
 int gckpp_gpu_set_option(gckpp_gpu_handle_t *handle, const char *key, int value);
 
