@@ -205,7 +205,7 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
     return;
   }
   BPROF(12);
-#if SMEM_EXACT_STEPS
+  if ((SMEM_EXACT_STEPS >> (OP == OP_VDOT ? 0 : OP == OP_JVS ? 1 : OP == OP_LUUPD ? 2 : 3)) & 1) {
   // only the bundle's maxlen term steps are applied (warp-uniform switches, one straight-line block per count so the
   // loads of a chunk still issue back to back): most bundles of the LU and sweep rounds carry one or two terms per
   // lane, and a pad step costs as many instructions as a real one
@@ -225,13 +225,13 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
       default: term(cc.x); break;
     }
   }
-#else
+  } else {
   term(c0.y); term(c0.z); term(c0.w);
   for (int k0 = 3; k0 < maxlen; k0 += 4) {
     const uint4 cc = rd.next();
     term(cc.x); term(cc.y); term(cc.z); term(cc.w);
   }
-#endif
+  }
   BPROF(13);
   for (int s = 0; s < lg; s++) {
 #pragma unroll
@@ -254,6 +254,41 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
     }
   }
   BPROF(15);
+}
+
+// The same bundle for ONE cell (cell-split rounds, see ros_smem.h): the warp reads the same table words and touches only
+// cell `cc`.  Whole chunks, like run_bundle.
+template <class M, int OP, class RD>
+__device__ __forceinline__ void run_bundle_cell(RD &rd, unsigned char *smem, const Slot *slot, int cc)
+{
+  using L = Lay<M>;
+  const uint4 c0 = rd.next();
+  const unsigned lw = c0.x;
+  const int row = lw & 0x1fff, maxlen = (lw >> 19) & 63, lg = (lw >> 25) & 7;
+  const unsigned char *Gb = smem + L::oG + cc * L::GS * 8, *Xb = smem + L::oX + cc * M::NVAR * 8;
+  double *Gc = reinterpret_cast<double *>(smem + L::oG) + cc * L::GS;
+  double *Xc = reinterpret_cast<double *>(smem + L::oX) + cc * M::NVAR;
+  auto ld = [](const unsigned char *base, unsigned off) { return *reinterpret_cast<const double *>(base + off); };
+  if (OP == OP_LUDIV) {
+    if ((lw >> 28) & 1) Gc[row] = Gc[row] / ld(Gb, c0.y & 0xffffu);
+    return;
+  }
+  double acc = 0.0;
+  auto term = [&](unsigned w) {
+    const unsigned hi = w >> 16, lo = w & 0xffffu;
+    if (OP == OP_LUUPD) acc = fma(ld(Gb, hi), ld(Gb, lo), acc);
+    else acc = fma(ld(Gb, hi), ld(Xb, lo), acc);
+  };
+  term(c0.y); term(c0.z); term(c0.w);
+  for (int k0 = 3; k0 < maxlen; k0 += 4) {
+    const uint4 c1 = rd.next();
+    term(c1.x); term(c1.y); term(c1.z); term(c1.w);
+  }
+  for (int s = 0; s < lg; s++) acc += __shfl_down_sync(FULLMASK, acc, 1 << s);
+  if ((lw >> 28) & 1) {
+    if (OP == OP_LUUPD) Gc[row] -= acc;
+    else Xc[row] -= acc;
+  }
 }
 
 // ---- tail block: one warp per cell ---------------------------------------------------------------------
@@ -463,8 +498,14 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   // a streamed round: this warp's bundles arrive in order through its ring
   auto stream_round = [&](auto opc, unsigned d) {
     const int nb = DIR_NB(d), W = DIR_W(d);
+    constexpr int OPV = decltype(opc)::value;
+    if (SMEM_CELL_SPLIT && (OPV == OP_SOLVE || OPV == OP_LUUPD || OPV == OP_LUDIV) && DIR_SPLIT(d)) {
+      // cell-split round: W = nb * NC warps, warp b * NC + c applies bundle b to cell c
+      if (warp < W) run_bundle_cell<M, (OPV == OP_SOLVE || OPV == OP_LUUPD || OPV == OP_LUDIV) ? OPV : OP_SOLVE>(rd, smem, slot, warp % NC);
+      return;
+    }
     if (warp < W)
-      for (int b = warp; b < nb; b += W) run_bundle<M, decltype(opc)::value>(rd, smem, slot, SCR);
+      for (int b = warp; b < nb; b += W) run_bundle<M, OPV>(rd, smem, slot, SCR);
   };
 
   for (;;) {
@@ -799,11 +840,11 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           if (r == n_tot) break;
           const unsigned d = dir[P.o_fwd + r];
 #ifdef SMEM_PROFILE
-          {
+          if (!DIR_SPLIT(d)) {
             const int nb = DIR_NB(d), W = DIR_W(d);
             if (warp < W)
               for (int b = warp; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR, (tid == 0 && blockIdx.x == 0) ? pacc_ : nullptr);
-          }
+          } else stream_round(std::integral_constant<int, OP_SOLVE>(), d);
 #else
           stream_round(std::integral_constant<int, OP_SOLVE>(), d);
 #endif
@@ -960,7 +1001,13 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   auto r1 = [&](int p) { return ph[2 * p + 1]; };
   if (r1(0) - r0(0) != 1 || r1(1) - r0(1) != 1) return -3;
   auto nbundles = [&](int r) { return (int)(S->rounds[3 * r + 1] - S->rounds[3 * r]); };
-  auto nwarps = [&](int r) { int nb = nbundles(r); return nb < NW ? nb : NW; };
+  // cell-split rounds (SMEM_CELL_SPLIT): at most NW / NC bundles, sweep rounds (phases 4, 5) and / or LU rounds (phase 2)
+  auto split = [&](int r) {
+    if (!SMEM_CELL_SPLIT || SMEM_SWEEP_RESIDENT || nbundles(r) * NC > NW) return false;
+    const bool sweep = (r >= r0(4) && r < r1(4)) || (r >= r0(5) && r < r1(5)), lu = r >= r0(2) && r < r1(2);
+    return (sweep && (SMEM_CELL_SPLIT & 1)) || (lu && (SMEM_CELL_SPLIT & 2));
+  };
+  auto nwarps = [&](int r) { int nb = nbundles(r); return split(r) ? nb * NC : (nb < NW ? nb : NW); };
   // directory: vdot, jvs, lu..., fwd..., bwd...
   std::vector<int> dr;
   dr.push_back(r0(0)); dr.push_back(r0(1));
@@ -1001,7 +1048,7 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
     int Wn = last ? NW : nwarps(dr[i + 1]);
     int Pb = last ? NW : (W > Wn ? W : Wn);
     uint32_t div = (S->rounds[3 * r + 2] & 0x10) ? 1u : 0u;
-    hp.dir[i] = DIR_PACK(nb, W, Pb, div, bfirst[i]);
+    hp.dir[i] = DIR_PACK(nb, W, Pb, div, bfirst[i]) | (split(r) ? 0x80000000u : 0u);
   }
   // per-warp streams in the order one Rodas3 attempt consumes them: vdot, jvs, lu rounds, [sweeps x2], vdot,
   // [sweeps], vdot, [sweeps]  (the sweeps only when their tables are not resident)
@@ -1019,9 +1066,16 @@ int smem_plan_build(int mech_id, const gckpp_host_tables_t *T, const gckpp_sched
   std::vector<std::vector<uint32_t>> ws(NW);
   for (auto &rw : order) {
     int r = rw.first, w0 = rw.second;
-    int W = nwarps(r);
-    if (w0 > 0 && W > NW - w0) W = NW - w0;
     uint32_t b0 = S->rounds[3 * r], b1 = S->rounds[3 * r + 1];
+    if (w0 == 0 && split(r)) {           // every bundle goes to NC warps (the shifted copy of the forward rounds is never split)
+      for (uint32_t b = b0; b < b1; b++)
+        for (int c = 0; c < NC; c++)
+          for (uint32_t row = S->brow[b]; row < S->brow[b + 1]; row++)
+            ws[(b - b0) * NC + c].insert(ws[(b - b0) * NC + c].end(), S->chunks + (size_t)row * 128, S->chunks + (size_t)(row + 1) * 128);
+      continue;
+    }
+    int W = split(r) ? (nbundles(r) < NW ? nbundles(r) : NW) : nwarps(r);
+    if (w0 > 0 && W > NW - w0) W = NW - w0;
     for (uint32_t b = b0; b < b1; b++) {
       int w = w0 + (int)((b - b0) % (uint32_t)W);
       for (uint32_t row = S->brow[b]; row < S->brow[b + 1]; row++)

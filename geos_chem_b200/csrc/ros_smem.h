@@ -37,11 +37,20 @@
 #ifndef SMEM_TAIL_SPANS
 #define SMEM_TAIL_SPANS 1
 #endif
-// apply exactly maxlen term steps per bundle instead of whole chunks (needs tables whose terms sit in the first maxlen
-// steps: kppgen/sched.py GCKPP_EXACT_STEPS=1).  Measured: 229 k cells/s against 239 k with whole chunks --
+// apply exactly maxlen term steps per bundle instead of whole chunks; bit mask over the ops (1 vdot, 2 jvs, 4 lu, 8 sweeps);
+// needs tables whose terms sit in the first maxlen steps for those ops: kppgen/sched.py GCKPP_EXACT_STEPS=<same mask>.  Measured: 229 k cells/s against 239 k with whole chunks --
 // a pad step is a broadcast load and costs less than the switches and the extra code
 #ifndef SMEM_EXACT_STEPS
 #define SMEM_EXACT_STEPS 0
+#endif
+// Cell-split rounds: a round with at most NW / NC bundles gives every bundle to NC warps, one cell each (warp b*NC + c).
+// A warp's shared-memory loads return through its own scheduler's 32 B/clk port (~9.5 cycles per LDS.64, measured), so
+// the 42 operand loads of a two-chunk bundle for three cells cost one warp ~400 cycles; split over three warps on three
+// schedulers they cost ~130.  Bit mask: 1 = sweep rounds, 2 = LU rounds.  Measured: the sweep rounds do not get faster
+// (240.0 k cells/s with or without), the small LU rounds do -- their division rounds are instruction-bound (3 IEEE
+// divisions per lane): 244.3 k with both.
+#ifndef SMEM_CELL_SPLIT
+#define SMEM_CELL_SPLIT (SMEM_SWEEP_RESIDENT ? 0 : 3)
 #endif
 #if SMEM_NC >= 4
 #define SMEM_SCR_GLOBAL 1
@@ -55,7 +64,8 @@
 #define DIR_W(d) ((int)(((d) >> 11) & 31u))
 #define DIR_P(d) ((int)(((d) >> 16) & 31u))
 #define DIR_DIV(d) ((int)(((d) >> 21) & 1u))
-#define DIR_BF(d) ((int)((d) >> 22))
+#define DIR_BF(d) ((int)(((d) >> 22) & 0x1ffu))
+#define DIR_SPLIT(d) ((int)((d) >> 31))
 #define DIR_PACK(nb, W, P, div, bf) ((uint32_t)(nb) | ((uint32_t)(W) << 11) | ((uint32_t)(P) << 16) | ((uint32_t)(div) << 21) | ((uint32_t)(bf) << 22))
 
 struct SmemArgs {

@@ -43,7 +43,7 @@ import numpy as np
 import os as _os
 LMAX = int(_os.environ.get('GCKPP_LMAX', 8))          # target number of terms per lane before a row is split over more lanes
 SOLVE_LMAX = int(_os.environ.get('GCKPP_SOLVE_LMAX', 7))    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
-EXACT_STEPS = int(_os.environ.get('GCKPP_EXACT_STEPS', 0))  # the kernel applies maxlen steps per bundle (SMEM_EXACT_STEPS), not whole chunks
+EXACT_STEPS = int(_os.environ.get('GCKPP_EXACT_STEPS', 0))   # bit mask of the ops whose bundles apply exactly maxlen steps: 1 vdot, 2 jvs, 4 lu, 8 sweeps  # the kernel applies maxlen steps per bundle (SMEM_EXACT_STEPS), not whole chunks
 BANK_GROUP = int(_os.environ.get('GCKPP_BANK_GROUP', 1))    # ... and choose which items share a half-warp
 BANK_OPT = int(_os.environ.get('GCKPP_BANK_OPT', 1))      # place the terms of a bundle against shared-memory bank conflicts
 TAIL = 32         # tail block size (one lane per tail row)
@@ -109,7 +109,7 @@ class Packer:
             b.lw = [meta[l][0] | (len(pieces[l]) << 13) | (maxlen << 19) | (lg << 25) | (meta[l][1] << 28) for l in range(32)]
             assert all(meta[l][0] < 8192 for l in range(32))
             if BANK_OPT and not (kind & K_DIV):
-                bank_optimize(b)
+                bank_optimize(b, kind)
             self.bundles.append(b)
         self.rounds.append((b0, len(self.bundles), kind))
 
@@ -126,10 +126,14 @@ def _bp(off):
     return (off >> 3) & 15
 
 
-def bundle_wavefronts(b):
+def _exact(kind):
+    return bool((EXACT_STEPS >> {0: 0, 1: 1, 2: 2}.get(kind & 7, 3)) & 1)
+
+
+def bundle_wavefronts(b, kind=4):
     """model: wavefronts of the operand gathers of one bundle and one cell (2 per instruction = conflict-free)"""
     nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
-    nstep = b.maxlen if EXACT_STEPS else nch * 4 - 1
+    nstep = b.maxlen if _exact(kind) else nch * 4 - 1
     tot = 0
     for s in range(nstep):
         for half in (0, 16):
@@ -143,13 +147,13 @@ def bundle_wavefronts(b):
     return tot, nstep * 4
 
 
-def bank_optimize(b, passes=3):
+def bank_optimize(b, kind=4, passes=3):
     """Re-place the terms of every lane over the bundle's term steps (positions beyond a lane's own terms hold the no-op
     pad word) so that, step by step, the lanes of a half-warp hit different bank pairs.  Greedy over the lanes, longest
     first, each lane an assignment problem (terms x steps) against the lanes already placed; a few refinement passes."""
     from scipy.optimize import linear_sum_assignment
     nch = 1 + max(0, (b.maxlen - 3 + 3) // 4)
-    nstep = b.maxlen if EXACT_STEPS else nch * 4 - 1
+    nstep = b.maxlen if _exact(kind) else nch * 4 - 1
     if b.maxlen == 0:
         return
     for half in (0, 16):
@@ -442,7 +446,7 @@ class Schedule:
             acc = np.zeros(32)
             first = ((words[:, 1] & 0xffff) >> 3).astype(np.int64) if words.shape[1] > 1 else np.zeros(32, np.int64)
             # the kernel applies maxlen term steps (EXACT_STEPS) or every word of every chunk (padding is a no-op)
-            nterm = min(maxlen, words.shape[1] - 1) if EXACT_STEPS else words.shape[1] - 1
+            nterm = min(maxlen, words.shape[1] - 1) if _exact({"vdot": 0, "jvs": 1, "lu": 2}.get(op, 4)) else words.shape[1] - 1
             for k in range(nterm if op not in ("div",) else 0):
                 w = words[:, 1 + k]
                 hi = ((w >> 16) >> 3).astype(np.int64)
