@@ -199,8 +199,10 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
   if (OP == OP_LUDIV) {
     if ((lw >> 28) & 1) {
       const unsigned dp = c0.y & 0xffffu;
+      // RECIP_DIAG tables: the pivot's diagonal already holds its reciprocal (written with its final update)
 #pragma unroll
-      for (int c = 0; c < NC; c++) G[c * L::GS + row] = G[c * L::GS + row] / ld(Gb + c * L::GS * 8, dp);
+      for (int c = 0; c < NC; c++)
+        G[c * L::GS + row] = M::RECIP_DIAG ? G[c * L::GS + row] * ld(Gb + c * L::GS * 8, dp) : G[c * L::GS + row] / ld(Gb + c * L::GS * 8, dp);
     }
     return;
   }
@@ -243,11 +245,29 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
 #pragma unroll
       for (int c = 0; c < NC; c++) X[c * M::NVAR + row] = acc[c];
     } else if (OP == OP_JVS) {
+      if (M::RECIP_DIAG && ((lw >> 30) & 1)) {       // a head pivot no LU update touches: final here, store 1/d (singular test :1985)
 #pragma unroll
-      for (int c = 0; c < NC; c++) G[c * L::GS + row] = (((lw >> 29) & 1) ? slot[c].ghinv : 0.0) - acc[c];
+        for (int c = 0; c < NC; c++) {
+          const double d = slot[c].ghinv - acc[c];
+          if (!(fabs(d) >= DBL_MIN)) const_cast<Slot *>(slot)[c].sing = 1;
+          G[c * L::GS + row] = 1.0 / d;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; c++) G[c * L::GS + row] = (((lw >> 29) & 1) ? slot[c].ghinv : 0.0) - acc[c];
+      }
     } else if (OP == OP_LUUPD) {
+      if (M::RECIP_DIAG && ((lw >> 30) & 1)) {       // the last update of a head pivot's diagonal
 #pragma unroll
-      for (int c = 0; c < NC; c++) G[c * L::GS + row] -= acc[c];
+        for (int c = 0; c < NC; c++) {
+          const double d = G[c * L::GS + row] - acc[c];
+          if (!(fabs(d) >= DBL_MIN)) const_cast<Slot *>(slot)[c].sing = 1;
+          G[c * L::GS + row] = 1.0 / d;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; c++) G[c * L::GS + row] -= acc[c];
+      }
     } else if (OP == OP_SOLVE) {
 #pragma unroll
       for (int c = 0; c < NC; c++) X[c * M::NVAR + row] -= acc[c];
@@ -270,7 +290,7 @@ __device__ __forceinline__ void run_bundle_cell(RD &rd, unsigned char *smem, con
   double *Xc = reinterpret_cast<double *>(smem + L::oX) + cc * M::NVAR;
   auto ld = [](const unsigned char *base, unsigned off) { return *reinterpret_cast<const double *>(base + off); };
   if (OP == OP_LUDIV) {
-    if ((lw >> 28) & 1) Gc[row] = Gc[row] / ld(Gb, c0.y & 0xffffu);
+    if ((lw >> 28) & 1) Gc[row] = M::RECIP_DIAG ? Gc[row] * ld(Gb, c0.y & 0xffffu) : Gc[row] / ld(Gb, c0.y & 0xffffu);
     return;
   }
   double acc = 0.0;
@@ -286,8 +306,13 @@ __device__ __forceinline__ void run_bundle_cell(RD &rd, unsigned char *smem, con
   }
   for (int s = 0; s < lg; s++) acc += __shfl_down_sync(FULLMASK, acc, 1 << s);
   if ((lw >> 28) & 1) {
-    if (OP == OP_LUUPD) Gc[row] -= acc;
-    else Xc[row] -= acc;
+    if (OP == OP_LUUPD) {
+      if (M::RECIP_DIAG && ((lw >> 30) & 1)) {
+        const double d = Gc[row] - acc;
+        if (!(fabs(d) >= DBL_MIN)) const_cast<Slot *>(slot)[cc].sing = 1;
+        Gc[row] = 1.0 / d;
+      } else Gc[row] -= acc;
+    } else Xc[row] -= acc;
   }
 }
 
@@ -706,10 +731,12 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           const int dp = diag[i], e = crow[i + 1];
 #pragma unroll
           for (int c = 0; c < NC; c++) {
-            const double d = G[c * L::GS + dp];
-            if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;          // also catches NaN from an earlier zero pivot
-            const double rdv = 1.0 / d;
-            G[c * L::GS + dp] = rdv;
+            double rdv = G[c * L::GS + dp];
+            if (!M::RECIP_DIAG) {
+              if (!(fabs(rdv) >= DBL_MIN)) slot[c].sing = 1;      // also catches NaN from an earlier zero pivot
+              rdv = 1.0 / rdv;
+              G[c * L::GS + dp] = rdv;
+            }
             for (int p = dp + 1; p < e; p++) G[c * L::GS + p] *= rdv;
           }
         };
@@ -727,16 +754,18 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         } else {
           // head rows: reciprocal diagonals first, then every U entry of the head rows scaled by it, spread
           // evenly over the threads (a thread per row would wait for the longest row)
-          for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
-            const int dp = diag[i];
+          if (!M::RECIP_DIAG) {
+            for (int i = tid - NC * 32; i < M::HEAD; i += NT - NC * 32) {
+              const int dp = diag[i];
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-              const double d = G[c * L::GS + dp];
-              if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;
-              G[c * L::GS + dp] = 1.0 / d;
+              for (int c = 0; c < NC; c++) {
+                const double d = G[c * L::GS + dp];
+                if (!(fabs(d) >= DBL_MIN)) slot[c].sing = 1;
+                G[c * L::GS + dp] = 1.0 / d;
+              }
             }
+            asm volatile("bar.sync 1, %0;" :: "n"((NW - NC) * 32) : "memory");
           }
-          asm volatile("bar.sync 1, %0;" :: "n"((NW - NC) * 32) : "memory");
           for (int q = tid - NC * 32; q < P.nuscale; q += NT - NC * 32) {
             const unsigned w = __ldg(P.uscale + q);
             const int p = w >> 16, dp = w & 0xffff;

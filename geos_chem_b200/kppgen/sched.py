@@ -44,6 +44,7 @@ import os as _os
 LMAX = int(_os.environ.get('GCKPP_LMAX', 8))          # target number of terms per lane before a row is split over more lanes
 SOLVE_LMAX = int(_os.environ.get('GCKPP_SOLVE_LMAX', 7))    # triangular sweeps: at most two chunks per bundle (3 + 4 terms), both prefetched before the barrier
 EXACT_STEPS = int(_os.environ.get('GCKPP_EXACT_STEPS', 0))   # bit mask of the ops whose bundles apply exactly maxlen steps: 1 vdot, 2 jvs, 4 lu, 8 sweeps  # the kernel applies maxlen steps per bundle (SMEM_EXACT_STEPS), not whole chunks
+RECIP_DIAG = int(_os.environ.get('GCKPP_RECIP_DIAG', 1))    # head pivots: reciprocal stored when the diagonal is final, L entries multiplied by it
 BANK_GROUP = int(_os.environ.get('GCKPP_BANK_GROUP', 1))    # ... and choose which items share a half-warp
 BANK_OPT = int(_os.environ.get('GCKPP_BANK_OPT', 1))      # place the terms of a bundle against shared-memory bank conflicts
 TAIL = 32         # tail block size (one lane per tail row)
@@ -98,7 +99,7 @@ class Packer:
                     lane = s * G + p
                     pieces[lane] = pc
                     f = (fl | 1) if p == 0 else (fl & ~1)
-                    meta[lane] = (row, f & 3)
+                    meta[lane] = (row, f & 7)
             maxlen = max(len(p) for p in pieces)
             assert maxlen < 64
             lg = G.bit_length() - 1
@@ -334,11 +335,6 @@ class Schedule:
         PAD_SUM, PAD_LU, PAD_SOLVE = (ncoef * 8) << 16, ((nnz * 8) << 16) | (nnz * 8), (nnz * 8) << 16
         P.add_round(vd, 0, pad=PAD_SUM)
         self.phase["vdot"] = (r0, len(P.rounds))
-        # ---- jvs ----------------------------------------------------------------------------
-        r0 = len(P.rounds)
-        # structural zeros (LU fill-in slots) are not listed: the kernel clears G before this round
-        P.add_round(jv, 1, pad=PAD_SUM)
-        self.phase["jvs"] = (r0, len(P.rounds))
         # ---- lu, head pivots ------------------------------------------------------------------
         # Fine-grained DAG of the row-wise elimination (the LU pattern is NOT structurally symmetric,
         # so pivot-row levels alone are not enough): DIV(k,j) waits for every update of G(k,j) and of
@@ -359,12 +355,34 @@ class Schedule:
                     upd_t[c] = max(upd_t.get(c, 0), tu + 1)
             for c, t in upd_t.items():
                 tfinal[(k, c)] = t
+        # RECIP_DIAG: the diagonal of a head pivot is replaced by its reciprocal by the item that gives it its final value
+        # (flag 4: the last LU update of G(j,j), or the Jacobian item when no update touches it), and the "div" rounds
+        # multiply by it -- one division per pivot instead of one per L entry.
+        inv_at = {}                     # level of the last update -> {diagonal positions}
+        inv_jvs = set()
+        if RECIP_DIAG:
+            for j in range(h):
+                t = tfinal.get((j, j), 0)
+                if t > 0:
+                    inv_at.setdefault(t - 1, set()).add(diag[j])
+                else:
+                    inv_jvs.add(diag[j])
+        self.recip_diag = bool(RECIP_DIAG)
+        self.inv_jvs = np.array(sorted(inv_jvs), np.int64)     # diagonals the Jacobian round leaves as reciprocals
+        # ---- jvs ----------------------------------------------------------------------------
+        r0 = len(P.rounds)
+        # structural zeros (LU fill-in slots) are not listed: the kernel clears G before this round
+        jv = [(k, tw, fl | (4 if k in inv_jvs else 0)) for k, tw, fl in jv]
+        P.add_round(jv, 1, pad=PAD_SUM)
+        self.phase["jvs"] = (r0, len(P.rounds))
         r0 = len(P.rounds)
         for t in range(max(list(divs_at) + list(upds_at) + [-1]) + 1):
             if t in divs_at:
                 P.add_round(divs_at[t], 2 | K_DIV)
             if t in upds_at:
-                P.add_round([(tg, tw, 0) for tg, tw in sorted(upds_at[t].items())], 2, pad=PAD_LU)
+                assert inv_at.get(t, set()) <= set(upds_at[t])
+                P.add_round([(tg, tw, 4 if tg in inv_at.get(t, ()) else 0) for tg, tw in sorted(upds_at[t].items())], 2, pad=PAD_LU)
+        assert all(t in upds_at for t in inv_at)
         self.phase["lu"] = (r0, len(P.rounds))
         # ---- scale U rows by the reciprocal diagonal ------------------------------------------
         # (done row-wise by the thread that inverts the diagonal: no table, see the kernel's post-LU pass)
@@ -441,7 +459,7 @@ class Schedule:
             ln = ((lw >> 13) & 0x3f).astype(np.int64)
             maxlen = int((lw[0] >> 19) & 0x3f)
             lg = int((lw[0] >> 25) & 7)
-            fl = ((lw >> 28) & 3).astype(np.int64)
+            fl = ((lw >> 28) & 7).astype(np.int64)
             assert ch.shape[0] == 1 + max(0, (maxlen + 0) // 4 if maxlen > 3 else 0) or True
             acc = np.zeros(32)
             first = ((words[:, 1] & 0xffff) >> 3).astype(np.int64) if words.shape[1] > 1 else np.zeros(32, np.int64)
@@ -467,13 +485,17 @@ class Schedule:
             elif op == "jvs":
                 G = kw["G"]
                 G[row[wr]] = -acc[wr] + np.where((fl[wr] & 2) != 0, kw["ghinv"], 0.0)
+                iv = wr & ((fl & 4) != 0)
+                G[row[iv]] = 1.0 / G[row[iv]]
             elif op == "lu":
                 G = kw["G"]
                 G[row[wr]] = G[row[wr]] - acc[wr]
+                iv = wr & ((fl & 4) != 0)
+                G[row[iv]] = 1.0 / G[row[iv]]
             elif op == "div":
                 G = kw["G"]
                 a = wr & (ln > 0)
-                G[row[a]] = G[row[a]] / G[first[a]]
+                G[row[a]] = (G[row[a]] * G[first[a]]) if self.recip_diag else (G[row[a]] / G[first[a]])
             elif op == "scale":
                 G = kw["G"]
                 a = wr & (ln > 0)
@@ -523,7 +545,10 @@ class Schedule:
                     G[p] = D[i, j]
                 else:
                     assert D[i, j] == 0.0
-        G[self.diag] = 1.0 / G[self.diag]
+        if self.recip_diag:
+            G[self.diag[self.h:]] = 1.0 / G[self.diag[self.h:]]       # the head diagonals are reciprocals already
+        else:
+            G[self.diag] = 1.0 / G[self.diag]
         for i in range(self.n):
             G[self.diag[i] + 1:self.crow[i + 1]] *= G[self.diag[i]]
         return G

@@ -64,13 +64,18 @@ def test_schedule_matches_oracle(mech):
     G = G[:-1]
     Gref = -jvs_o.copy()
     Gref[np.array(m.lu_diag)] += ghinv
-    np.testing.assert_allclose(G, Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
+    # RECIP_DIAG tables: the diagonals of head pivots that no LU update touches leave the Jacobian round as reciprocals
+    Gcmp = G.copy()
+    Gcmp[s.inv_jvs] = 1.0 / Gcmp[s.inv_jvs]
+    np.testing.assert_allclose(Gcmp, Gref, rtol=1e-11, atol=1e-13 * np.abs(Gref).max())
     # LU + solve against the oracle's KppDecomp / KppSolve
     lu_o, ier = o.decomp(mech, Gref)
     assert ier == 0
     b = rng.standard_normal(m.nvar) * np.abs(vdot_o).max()
     x_o = o.solve(mech, lu_o, b)
-    Glu = s.emulate_lu(np.append(Gref, 0.0))
+    Gin = np.append(Gref, 0.0)
+    Gin[s.inv_jvs] = 1.0 / Gin[s.inv_jvs]
+    Glu = s.emulate_lu(Gin)
     x = s.emulate_solve(Glu, b.copy())
     assert Glu[-1] == 0.0
     Glu = Glu[:-1]
