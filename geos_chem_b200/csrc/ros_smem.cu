@@ -67,6 +67,7 @@ struct Slot {
   int out_cell, in_cell, out_ierr, pad_;
   int ist[8], out_ist[8];
   double out_r[3];
+  double hc[6];        // C(k) / (Direction * H) of this attempt (the stage right-hand sides, :704-709), computed once per slot
 };
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -576,6 +577,8 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
       s.sing = 0;
       s.accept = 0;
       s.ghinv = 1.0 / (Dir * s.H * o.Gamma[0]);
+#pragma unroll
+      for (int k = 0; k < 6; k++) s.hc[k] = o.C[k] / (Dir * s.H);
       if (!s.skip && s.newstep) {
         s.ist[Nfun]++;
         if (!o.Autonomous) s.ist[Nfun]++;
@@ -625,9 +628,6 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
     }
     if (!any) break;
     PROF(0);
-    double dh[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) dh[c] = Dir * slot[c].H;
     // Three function evaluations per attempt (Rodas3: NewF = T,F,T,T; :691-724): Fcn0 (followed by the
     // Jacobian, the LU and stages 1-2), stage 3, stage 4.  One copy of the Fun and solve code.
 #pragma unroll 1
@@ -801,9 +801,9 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           for (int c = 0; c < NC; c++) {
             double v;
             if (st == 0) v = F0[c];
-            else if (st == 1) v = fma(o.C[0] / dh[c], K1[c], F0[c]);
-            else if (st == 2) v = fma(o.C[2] / dh[c], K2[c], fma(o.C[1] / dh[c], K1[c], X[c * N + tid]));
-            else v = fma(o.C[5] / dh[c], K3[c], fma(o.C[4] / dh[c], K2[c], fma(o.C[3] / dh[c], K1[c], X[c * N + tid])));
+            else if (st == 1) v = fma(slot[c].hc[0], K1[c], F0[c]);
+            else if (st == 2) v = fma(slot[c].hc[2], K2[c], fma(slot[c].hc[1], K1[c], X[c * N + tid]));
+            else v = fma(slot[c].hc[5], K3[c], fma(slot[c].hc[4], K2[c], fma(slot[c].hc[3], K1[c], X[c * N + tid])));
             if (AR && !((mk >> c) & 1u)) v = 0.0;
             X[c * N + tid] = v;
           }
