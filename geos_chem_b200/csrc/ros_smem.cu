@@ -472,7 +472,9 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   const uint32_t *ar_rowcol = reinterpret_cast<const uint32_t *>(a.ar_keep_spc);
   unsigned mk = 0xffffffffu;                                                 // bit c: species tid of slot c is kept
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index through a broadcast: the compiler then knows it is warp-uniform and drops the divergence checks
+  // (BRA.DIV / WARPSYNC) around the shuffles and barriers of the warp-conditional regions
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULLMASK, tid >> 5, 0);
   const RosOpts &o = a.o;
   const double Dir = (double)o.Direction;
 

@@ -1,6 +1,4 @@
 #!/bin/bash
-bash tools/gpu_round.sh r02as
-o=gpurun_out/r02as
-( timeout 600 python bench.py --config 1 --steps 3 --warmup 3 --no-cpu-baseline ) > $o/bench_config1.log 2>&1; tail -n 1 $o/bench_config1.log | cut -c1-200
-( timeout 600 python bench.py --hstart cold --steps 2 --warmup 3 --no-cpu-baseline ) > $o/bench_cold.log 2>&1; tail -n 1 $o/bench_cold.log | cut -c1-200
-( timeout 900 python bench.py --config 5-ar --steps 3 --warmup 3 ) > $o/bench_ar.log 2>&1; tail -n 1 $o/bench_ar.log | cut -c1-200
+o=gpurun_out/r02au; mkdir -p $o
+( VB_ITERS=3 timeout 300 python tools/variant_bench.py own ) > $o/variant_uniform_warp.log 2>&1; tail -n 1 $o/variant_uniform_warp.log
+( time timeout 1200 python -m pytest tests -m gpu -x -q -s -k "parity or fixture or autoreduce" ) > $o/pytest_gpu.log 2>&1; grep -E "passed|failed|Error|^E |different steps [1-9]" $o/pytest_gpu.log | head -20
