@@ -169,7 +169,14 @@ __device__ __forceinline__ void run_bundle(RD &rd, unsigned char *smem, const Sl
   double *X = reinterpret_cast<double *>(smem + L::oX);
   const uint4 c0 = rd.next();
   const unsigned lw = c0.x;
+#if SMEM_UNIFORM_LW
+  // maxlen and log2(g) are the same in every lane of a bundle: taken from lane 0 through a broadcast, the chunk loop and
+  // the shuffle loop become warp-uniform for the compiler (no divergence checks around the shuffles)
+  const unsigned lwu = __shfl_sync(FULLMASK, lw, 0);
+  const int row = lw & 0x1fff, maxlen = (lwu >> 19) & 63, lg = (lwu >> 25) & 7;
+#else
   const int row = lw & 0x1fff, maxlen = (lw >> 19) & 63, lg = (lw >> 25) & 7;
+#endif
   double acc[NC];
 #pragma unroll
   for (int c = 0; c < NC; c++) acc[c] = 0.0;
@@ -285,7 +292,12 @@ __device__ __forceinline__ void run_bundle_cell(RD &rd, unsigned char *smem, con
   using L = Lay<M>;
   const uint4 c0 = rd.next();
   const unsigned lw = c0.x;
+#if SMEM_UNIFORM_LW
+  const unsigned lwu = __shfl_sync(FULLMASK, lw, 0);
+  const int row = lw & 0x1fff, maxlen = (lwu >> 19) & 63, lg = (lwu >> 25) & 7;
+#else
   const int row = lw & 0x1fff, maxlen = (lw >> 19) & 63, lg = (lw >> 25) & 7;
+#endif
   const unsigned char *Gb = smem + L::oG + cc * L::GS * 8, *Xb = smem + L::oX + cc * M::NVAR * 8;
   double *Gc = reinterpret_cast<double *>(smem + L::oG) + cc * L::GS;
   double *Xc = reinterpret_cast<double *>(smem + L::oX) + cc * M::NVAR;

@@ -52,6 +52,9 @@
 #ifndef SMEM_CELL_SPLIT
 #define SMEM_CELL_SPLIT (SMEM_SWEEP_RESIDENT ? 0 : 3)
 #endif
+#ifndef SMEM_UNIFORM_LW
+#define SMEM_UNIFORM_LW 1
+#endif
 #if SMEM_NC >= 4
 #define SMEM_SCR_GLOBAL 1
 #else
