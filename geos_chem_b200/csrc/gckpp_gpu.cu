@@ -684,6 +684,7 @@ static int run_integrator(gckpp_gpu_handle *h, const Decoded &d, int ncell, int 
       a.ar_keep_spc = reinterpret_cast<const unsigned char *>(h->sm_rowcol.p);
       h->stats[6] += 1;
     }
+    CUDA_TRY(smem_set_directory(h->mech_id, h->plan.dir.data(), (int)h->plan.dir.size(), h->stream));     // per device, 250 bytes
     CUDA_TRY(launch_ros_smem(h->mech_id, h->sargs, a, nb, h->stream, d.autoreduce != 0));
     if (d.autoreduce) {
       CUDA_TRY(launch_ar_first_order(h->M, a, h->ar_mask.as<unsigned char>(), h->stream));

@@ -54,6 +54,13 @@
 #define PROF(i) do { } while (0)
 #endif
 
+// The round directory in constant memory (one slot per mechanism): a constant load with a warp-uniform index lands in a
+// uniform register, so everything decoded from a directory entry (bundles, warps, barrier size, flags) is warp-uniform for
+// the compiler and the round-level branches are uniform branches.  Set per device before a launch (smem_set_directory).
+#if SMEM_CONST_DIR
+__constant__ uint32_t c_round_dir[2][128];
+#endif
+
 namespace {
 
 constexpr int NC = SMEM_NC, NW = SMEM_NW, RS = SMEM_RS, NT = NW * 32;
@@ -494,7 +501,12 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
   for (int i = tid; i < P.res_rows * 32; i += NT) RES[i] = P.resident[i];
   for (int i = tid; i < 32 * 32; i += NT) tposT[i] = P.tpos[i];
   for (int i = tid; i < P.nresb; i += NT) boff[i] = P.boff[i];
+#if SMEM_CONST_DIR
+  const uint32_t *dirc = c_round_dir[std::is_same<M, fullchem_dims>::value ? 0 : 1];
+#else
   for (int i = tid; i < P.ndir; i += NT) dir[i] = P.dir[i];
+  const uint32_t *dirc = dir;
+#endif
   for (int i = tid; i < N; i += NT) diag[i] = P.diag[i];
   for (int i = tid; i <= N; i += NT) crow[i] = P.crow[i];
   for (int i = tid; i < NC * L::NYG; i += NT) {
@@ -682,7 +694,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         }
       }
       __syncthreads();
-      stream_round(std::integral_constant<int, OP_VDOT>(), dir[0]);
+      stream_round(std::integral_constant<int, OP_VDOT>(), dirc[0]);
       __syncthreads();
       PROF(1);
       if (ip == 0) {
@@ -714,7 +726,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         }
         for (int i = tid; i < NC * L::GS; i += NT) G[i] = 0.0;        // structural zeros / fill-in slots / zero slot
         __syncthreads();
-        stream_round(std::integral_constant<int, OP_JVS>(), dir[1]);
+        stream_round(std::integral_constant<int, OP_JVS>(), dirc[1]);
         __syncthreads();
         if (AR) {
           for (int k = tid; k < M::NNZ; k += NT) {
@@ -732,7 +744,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         // ---- sparse LU  (KppDecomp): head pivots by DAG level, then the tail block
 #pragma unroll 1
         for (int r = 0; r < P.n_lu; r++) {
-          const unsigned d = dir[P.o_lu + r];
+          const unsigned d = dirc[P.o_lu + r];
           if (DIR_DIV(d)) stream_round(std::integral_constant<int, OP_LUDIV>(), d);
           else stream_round(std::integral_constant<int, OP_LUUPD>(), d);
           round_barrier(DIR_P(d), warp);
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
           }
 #pragma unroll 1
           for (int r = 0; r < P.n_fwd; r++) {
-            const unsigned d = dir[P.o_fwd1 + r];
+            const unsigned d = dirc[P.o_fwd1 + r];
             const int nb = DIR_NB(d), W = DIR_W(d), wv = warp - NC;
             if (wv < W)
               for (int b = wv; b < nb; b += W) run_bundle<M, OP_SOLVE>(rd, smem, slot, SCR);
@@ -847,7 +859,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         auto prefetch = [&](int r, unsigned &d, PreReader &pr) {
           d = 0; pr.n = 0; pr.p = RES + lane;
           if (r < n_tot) {
-            d = dir[P.o_fwd + r];
+            d = dirc[P.o_fwd + r];
             if (warp < DIR_W(d)) {
               const uint4 *p = RES + (size_t)boff[DIR_BF(d) + warp] * 32 + lane;
               pr.c0 = p[0]; pr.c1 = p[32]; pr.p = p + 64;
@@ -881,7 +893,7 @@ __global__ void __launch_bounds__(NT, 1) ros_smem_kernel(SmemArgs P, RosArgs a)
         for (int r = fwd_done ? P.n_fwd : 0;; r++) {
           if (r == P.n_fwd) tails();
           if (r == n_tot) break;
-          const unsigned d = dir[P.o_fwd + r];
+          const unsigned d = dirc[P.o_fwd + r];
 #ifdef SMEM_PROFILE
           if (!DIR_SPLIT(d)) {
             const int nb = DIR_NB(d), W = DIR_W(d);
@@ -1173,6 +1185,18 @@ static cudaError_t launch_t(const SmemArgs &P, const RosArgs &a, int blocks, cud
   if (e != cudaSuccess) return e;
   k<<<blocks, NT, P.s_total, s>>>(P, a);
   return cudaGetLastError();
+}
+
+cudaError_t smem_set_directory(int mech_id, const uint32_t *dir, int n, cudaStream_t s)
+{
+#if SMEM_CONST_DIR
+  if (n > 128 || (mech_id != GCKPP_MECH_FULLCHEM && mech_id != GCKPP_MECH_HG)) return cudaErrorInvalidValue;
+  return cudaMemcpyToSymbolAsync(c_round_dir, dir, sizeof(uint32_t) * (size_t)n, sizeof(uint32_t) * 128 * (mech_id == GCKPP_MECH_FULLCHEM ? 0 : 1),
+                                 cudaMemcpyHostToDevice, s);
+#else
+  (void)mech_id; (void)dir; (void)n; (void)s;
+  return cudaSuccess;
+#endif
 }
 
 cudaError_t launch_ros_smem(int mech_id, const SmemArgs &P, const RosArgs &a, int blocks, cudaStream_t s, bool autoreduce)
