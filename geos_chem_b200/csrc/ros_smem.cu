@@ -104,6 +104,9 @@ struct Reader {
   const uint4 *gsrc;        // this lane's column of the warp's stream
   uint32_t ring;            // shared-space byte address of this lane's column of the warp's ring
   int L, irow, islot, cslot;
+#if SMEM_RING_PRELOAD
+  uint4 pre;                // the next chunk row, already in registers (see next())
+#endif
   __device__ __forceinline__ void issue()
   {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;"
@@ -111,18 +114,39 @@ struct Reader {
     if (++irow == L) irow = 0;
     if (++islot == RS) islot = 0;
   }
+  __device__ __forceinline__ uint4 lds()
+  {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + cslot * 512));
+    if (++cslot == RS) cslot = 0;
+    return v;
+  }
   __device__ __forceinline__ void prime()
   {
     for (int i = 0; i < RS - 1; i++) issue();
+#if SMEM_RING_PRELOAD
+    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 2));
+    pre = lds();
+#endif
   }
+  // SMEM_RING_PRELOAD: the ring read is software-pipelined -- next() hands out the row loaded by the previous call and starts
+  // the load of the following one, so neither the first chunk of a bundle (right after a round barrier) nor its second chunk
+  // waits for an LDS.128.  Row k+3 is copied into the slot of row k-1, which was read two calls ago: the look-ahead stays
+  // three rows (one in registers, two in flight).
   __device__ __forceinline__ uint4 next()
   {
-    uint4 v;
+#if SMEM_RING_PRELOAD
+    const uint4 v = pre;
+    issue();
     asm volatile("cp.async.wait_group %0;" :: "n"(RS - 2));
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring + cslot * 512));
-    if (++cslot == RS) cslot = 0;
+    pre = lds();
+    return v;
+#else
+    asm volatile("cp.async.wait_group %0;" :: "n"(RS - 2));
+    const uint4 v = lds();
     issue();
     return v;
+#endif
   }
 };
 
