@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from geos_chem_b200 import kpp
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
@@ -67,3 +69,24 @@ def test_smem_kernel_plan_fits_b200(lib):
     p = kpp.plan_info("fullchem")
     # head/tail split of the elimination DAG: 21 LU rounds and 19 sweep rounds instead of 72 + 68 levels
     assert (p["n_lu"], p["n_fwd"], p["n_bwd"]) == (21, 10, 9)
+
+
+def test_production_kernel_sass_has_no_divergence_checks_or_spills(lib):
+    """The block kernel's control flow is warp-uniform for the compiler (warp index and bundle length come through
+    broadcasts, csrc/ros_smem.cu): its SASS must contain no BRA.DIV / WARPSYNC and no local-memory traffic.  Those
+    scaffolds cost 8 % of the kernel's throughput when they crept in (profiles/r02au_*, r02av_*)."""
+    import shutil
+    import subprocess
+    obj = os.path.join(os.path.dirname(kpp.LIB_PATH), "csrc", "build", "ros_smem.o")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(obj) or not os.path.exists(cuobjdump):
+        pytest.skip("no object file / cuobjdump (the library was built elsewhere)")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    blocks = sass.split("Function : ")
+    prod = [b for b in blocks if "ros_smem_kernel" in b.split("\n", 1)[0] and "fullchem_dims" in b.split("\n", 1)[0]]
+    assert len(prod) == 2, [b.split("\n", 1)[0] for b in blocks[1:]]          # the plain and the auto-reduce instance
+    for b in prod:
+        name = b.split("\n", 1)[0]
+        assert "BRA.DIV" not in b and "WARPSYNC" not in b, name
+        assert " LDL" not in b and " STL" not in b, name
+        assert "DFMA" in b and "LDGSTS" in b, name
