@@ -1,4 +1,4 @@
 #!/bin/bash
-# last visit of round 2: the driver's smoke() on the final build
-o=gpurun_out/r02ba; mkdir -p $o
-( time timeout 100 python -c "import __graft_entry__ as g; g.smoke()" ) > $o/smoke.log 2>&1; tail -n 5 $o/smoke.log
+# One GPU-box visit with everything the evidence index (profiles/README.md) expects:
+#   bash gpurun_probe.sh [tag]    ->  gpurun_out/<tag>/ ; then `python tools/summarize_round.py <tag>` copies it into profiles/
+bash tools/gpu_round.sh ${1:-r03a}
